@@ -1,0 +1,88 @@
+"""CPU: the oracle restatement against (a) the reference's own doctest known answers and
+(b) golden outputs produced by executing the reference code (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+from oracle import camera_oracle, cvc_oracle, raypool_oracle, surfacenet_oracle
+from tests import util
+
+
+def test_perspectiveProj_reference_doctest_known_answers():
+    # utils/camera.py:144-160 -- the only known answers the reference pins on this path
+    np.random.seed(201611)
+    Ms = np.random.rand(2, 3, 4)
+    pts_3D = np.random.rand(2, 3)
+    pts_2Dh, pts_2Dw = camera_oracle.perspectiveProj(Ms, pts_3D, return_int_hw=False)
+    assert np.allclose(pts_2Dw, np.array([[1.35860185, 0.9878389], [0.64522543, 0.76079278]]))
+    pts_2Dh_int, pts_2Dw_int = camera_oracle.perspectiveProj(Ms, pts_3D, return_int_hw=True)
+    assert np.allclose(pts_2Dw_int, np.array([[1, 1], [1, 1]]))
+    assert np.allclose(np.r_[camera_oracle.perspectiveProj(Ms[1], pts_3D[0], return_int_hw=False)],
+                       np.stack((pts_2Dh, pts_2Dw))[:, 1, 0])
+
+
+def test_perspectiveProj_errors():
+    with pytest.raises(ValueError):
+        camera_oracle.perspectiveProj(np.zeros((4, 4)), np.zeros((2, 3)))
+    with pytest.raises(ValueError):
+        camera_oracle.perspectiveProj(np.zeros((3, 4)), np.zeros((2, 2)))
+
+
+def test_perspectiveProj_golden(golden, cams):
+    h, w = camera_oracle.perspectiveProj(golden["pp_doctest_Ms"], golden["pp_doctest_pts"], return_int_hw=False)
+    assert np.array_equal(h, golden["pp_doctest_h"]) and np.array_equal(w, golden["pp_doctest_w"])
+    h, w, d = camera_oracle.perspectiveProj(cams[golden["pp_dtu_views"]], golden["pp_dtu_pts"], True, True)
+    assert h.dtype == np.int64
+    assert np.array_equal(h, golden["pp_dtu_h"]) and np.array_equal(w, golden["pp_dtu_w"])
+    assert np.array_equal(d, golden["pp_dtu_depth"])
+    hw = camera_oracle.perspectiveProj(cams[3], golden["pp_dtu_pts"][0], return_int_hw=False)
+    assert np.array_equal(np.r_[hw], golden["pp_dtu_single_hw"])
+
+
+@pytest.mark.parametrize("name", ["basic", "ragged_sizes", "dup_views", "c1_s32", "outside"])
+def test_cvc_oracle_matches_reference_outputs(golden, cams, name):
+    case = util.cvc_cases(cams)[name]
+    X = cvc_oracle.gen_coloredCubes(case["pairs"], case["xyz"], case["resol"], case["cameraPOs"], case["images"], case["D"])
+    assert X.dtype == np.float32 and X.shape == golden["cvc_" + name].shape
+    assert np.array_equal(X, golden["cvc_" + name].astype(np.float32))
+    _, X2 = cvc_oracle.preprocess_augmentation(None, X, util.MEAN6[None, :, None, None, None], False, False)
+    assert X2.dtype == np.float32
+    assert np.array_equal(X2.reshape(-1)[::997], golden["cvc_" + name + "_pre_sample"])
+    assert X2.astype(np.float64).sum() == golden["cvc_" + name + "_pre_sum"][0]
+
+
+def test_cvc_cases_cover_out_of_scope(golden):
+    # the ragged case must really exercise the zero fill, the basic case must be fully in scope
+    assert (golden["cvc_ragged_sizes"].reshape(4, 2, 3, -1).max(axis=2) == 0).mean() > 0.05
+    assert golden["cvc_outside"].max() == 0
+
+
+@pytest.mark.parametrize("name", ["sheet16", "sheet32_dup", "ties", "lowres_collide", "all_ones", "empty",
+                                  "none_thresh_f32", "exact_thresh"])
+def test_raypool_oracle_matches_reference_outputs(golden, cams, name):
+    case = util.raypool_cases(cams)[name]
+    votes = raypool_oracle.rayPooling_1cube_numpy(case["cameraPOs"], None, case["pred"], case["pairs"], case["xyz"],
+                                                  case["resol"], prediction_thresh=case["thresh"])
+    assert np.array_equal(votes.astype(np.uint8), golden["rp_" + name])
+    assert votes.max() <= 2 * case["pairs"].shape[0]
+
+
+def test_raypool_oracle_bad_dims():
+    with pytest.raises(ValueError):
+        raypool_oracle.rayPooling_1cube_numpy(np.zeros((2, 3, 4)), None, np.zeros((2, 2, 4, 4, 4)), np.array([[0, 1]]),
+                                              np.zeros(3, np.float32), np.float32(1))
+
+
+def test_upsample_kernels_match_reference(golden):
+    from surfacenet_b200 import weights
+    for k in (3, 5):
+        assert np.array_equal(surfacenet_oracle.W_5D(k), golden["W5D_%d" % k])
+        assert np.array_equal(weights.upsample_W(k), golden["W5D_%d" % k])
+
+
+def test_upsample_micro_cases():
+    # zero-stuff + fixed taps, 'same' zero border
+    import torch
+    x = torch.zeros(1, 1, 2, 2, 2); x[0, 0, :, 0, 0] = torch.tensor([1.0, 2.0])
+    y4 = surfacenet_oracle.upsample(x, surfacenet_oracle.W_5D(5), 4)[0, 0, :, 0, 0].numpy()
+    assert np.allclose(y4, [1, 2 / 3, 1.0, 4 / 3, 2, 4 / 3, 2 / 3, 0], atol=1e-6)
+    y2 = surfacenet_oracle.upsample(x, surfacenet_oracle.W_5D(3), 2)[0, 0, :, 0, 0].numpy()
+    assert np.allclose(y2, [1, 1.5, 2, 1.0], atol=1e-6)

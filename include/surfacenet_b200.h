@@ -1,0 +1,169 @@
+/*
+ * surfacenet_b200 -- C ABI of the B200-native SurfaceNet per-cube inference hot path.
+ *
+ * Every entry point replaces one Python-level interface of the reference (mjiUST/SurfaceNet,
+ * paths relative to the reference root); the reference has no FFI of its own (it is pure
+ * Python driving Theano/cuDNN), so the "binding a maintainer would add" is the ctypes stub shown
+ * in INTEGRATION.md and implemented in surfacenet_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only.  `*_dev` pointers are CUDA device pointers on the current
+ *     device, `*_host` pointers are host memory (pinned memory makes the copies asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *     points only enqueue work on `stream`; they never synchronise unless stated.
+ *   - return value: SN_OK or a negative SN_ERR_* code; sn_last_error() gives the message of the
+ *     last failure on the calling thread.  The Python layer maps SN_ERR_INVALID -> ValueError
+ *     (the reference raises ValueError for bad shapes: utils/rayPooling.py:201-202,
+ *     utils/camera.py:163-170) and everything else -> RuntimeError.
+ *   - volumes are C-order (x, y, z) with z fastest, exactly the reference's meshgrid('ij')
+ *     flattening (utils/CVC.py:15-20).
+ */
+#ifndef SURFACENET_B200_H
+#define SURFACENET_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SN_OK            0
+#define SN_ERR_INVALID  (-1)   /* bad argument / shape                       -> ValueError   */
+#define SN_ERR_CUDA     (-2)   /* CUDA runtime error                         -> RuntimeError */
+#define SN_ERR_DOMAIN   (-3)   /* input outside the supported numeric domain -> ValueError   */
+#define SN_ERR_NOMEM    (-4)   /* workspace too small                        -> RuntimeError */
+
+#define SN_MODE_FP32     0     /* CUDA-core fp32 convolutions (exact reference precision)        */
+#define SN_MODE_TC_EXACT 1     /* tcgen05, fp16 hi+lo split operands, 3 MMAs / product           */
+#define SN_MODE_TC_FAST  2     /* tcgen05, single-pass fp16 operands (does NOT meet 1e-4 parity) */
+
+#define SN_ACT_RELU      0
+#define SN_ACT_SIGMOID   1
+#define SN_ACT_NONE      2
+
+const char* sn_last_error(void);
+int         sn_version(void);
+/* number of kernels this library has launched since load / since the last reset (bench: gpu_launches) */
+int64_t     sn_launch_count(void);
+void        sn_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * utils/camera.py:123-184  perspectiveProj(projection_M, xyz_3D, return_int_hw, return_depth)
+ *   P_dev   (n_mats,3,4) f64;  xyz_dev (n_pts,3) f64
+ *   h_out_dev, w_out_dev, depth_out_dev : (n_mats,n_pts) f64 (depth_out_dev may be NULL).
+ *   round_to_int != 0 -> h, w are rint()-ed (half to even) as `.round()` does at camera.py:179;
+ *   the caller casts to int64.
+ */
+int sn_perspective_proj(const double* P_dev, int n_mats, const double* xyz_dev, int64_t n_pts, int round_to_int,
+                        double* h_out_dev, double* w_out_dev, double* depth_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * utils/CVC.py:6-53,56-104  __colorize_cube__ / gen_coloredCubes   (+ :108-111 mean subtraction)
+ *   images_dev   packed uint8 RGB images, view v is (H_v, W_v, 3) row-major at images_dev+img_offset[v]
+ *   img_offset_dev (V) i64, img_hw_dev (V,2) i32 = (H_v, W_v);  views never referenced may have H=W=0
+ *   P_dev        (V,3,4) f64 camera matrices, indexed by view position (main_reconstruct.py:48)
+ *   xyz_dev      (B,3) f32 cube min corners;  resol_dev (B) f32
+ *   views_dev    (B, 2*n_vp) i32 = selected_viewPairs[b].flatten()   (CVC.py:82)
+ *   X_out_dev    (B*n_vp, 6, D,D,D) f32, channel order [A.R,A.G,A.B,B.R,B.G,B.B] (CVC.py:47,67,104), may be NULL
+ *   mean6_dev    NULL -> raw colours (gen_coloredCubes);  (6) f32 -> X - mean (preprocess_augmentation, CVC.py:110-111)
+ *   idx_w_out_dev, idx_h_out_dev (B, 2*n_vp, D^3) i32 and in_scope_out_dev (same shape) u8: the
+ *                voxel -> pixel index map of CVC.py:39-45 (all three NULL or all three set; for tests)
+ */
+int sn_cvc_gather(const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev, int n_views,
+                  const double* P_dev, const float* xyz_dev, const float* resol_dev, const int32_t* views_dev,
+                  int n_cubes, int n_vp, int D, const float* mean6_dev, float* X_out_dev,
+                  int32_t* idx_w_out_dev, int32_t* idx_h_out_dev, uint8_t* in_scope_out_dev, void* stream);
+
+/* elementwise X[n,c,...] -= mean[c]  (utils/CVC.py:110-111 on an existing tensor) */
+int sn_sub_channel_mean(float* X_dev, int64_t n, int channels, int64_t spatial, const float* mean_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * nets/SurfaceNet.py:385-402  SurfaceNet_inference(...) -> (viewPair_relativeImpt_fn, nViewPair_SurfaceNet_fn)
+ *
+ * sn_net_create  = build + lasagne.layers.set_all_param_values(...) (SurfaceNet.py:397-400): takes the
+ *   flat list of 105 float32 host arrays in get_all_param_values order (layout: SURVEY.md App. B,
+ *   surfacenet_b200/weights.py); element counts are validated against the architecture.
+ */
+typedef struct sn_net sn_net;
+int  sn_net_create(const float* const* arrays_host, const int64_t* sizes, int n_arrays, sn_net** out);
+void sn_net_destroy(sn_net* net);
+
+/* bytes of device workspace sn_net_forward needs for (n_pair_cubes, D, mode) */
+int64_t sn_net_workspace_bytes(const sn_net* net, int n_pair_cubes, int D, int mode);
+
+/* nViewPair_SurfaceNet_fn(X[, w])  (SurfaceNet.py:343-383; main_reconstruct.py:145-146)
+ *   X_dev        (n_cubes*n_vp, 6, D,D,D) f32, mean already subtracted
+ *   w_dev        (n_cubes, n_vp) f32 or NULL (NULL only when n_vp == 1: SurfaceNet.py:354-357)
+ *   fused_out_dev   (n_cubes, 1, D,D,D) f32   = sum_v (w/sum w) p   (nets/layers.py:325-336)
+ *   unfused_out_dev (n_cubes, n_vp, D,D,D) f32 (may be NULL)
+ */
+int sn_net_forward(const sn_net* net, const float* X_dev, int n_cubes, int n_vp, int D, const float* w_dev,
+                   float* fused_out_dev, float* unfused_out_dev, void* workspace_dev, int64_t workspace_bytes,
+                   int mode, void* stream);
+
+/* viewPair_relativeImpt_fn(features, n_samples_perGroup)  (nets/SurfaceNet.py:84-100,337)
+ *   features_dev (n_rows, 258) f32 -> out_dev (n_rows / n_per_group, n_per_group) f32 softmax weights */
+int sn_net_relative_importance(const sn_net* net, const float* features_dev, int64_t n_rows, int n_per_group,
+                               float* out_dev, void* stream);
+
+/* single layers, exposed for per-kernel parity tests and calibration (NCDHW fp32):
+ *   conv + BatchNorm(inference) + activation: nets/SurfaceNet.py:33-74 units; `unit` indexes
+ *   surfacenet_b200/weights.py:UNITS.  in (n,C_in,S,S,S) -> out (n,C_out,S,S,S). */
+int sn_net_layer_conv(const sn_net* net, int unit, const float* in_dev, int n, int S, float* out_dev, void* stream);
+int sn_maxpool2(const float* in_dev, int n, int C, int S, float* out_dev, void* stream);      /* SurfaceNet.py:37,46 */
+/* nets/layers.py:376-390: zero-stuff by f, k^3 fixed conv (W from the parameter list), 'same'.
+ *   in (n,C,S,S,S) -> written into out (n, C_total, fS,fS,fS) at channel offset c_off. */
+int sn_net_layer_upsample(const sn_net* net, int unit, const float* in_dev, int n, int C, int S, float* out_dev,
+                          int C_total, int c_off, void* stream);
+/* nets/layers.py:321-339 ChannelPool_weightedAverage:  p (n_cubes,n_vp,vol) , w (n_cubes,n_vp) -> (n_cubes,vol) */
+int sn_fuse_weighted_average(const float* p_dev, const float* w_dev, int n_cubes, int n_vp, int64_t vol, float* out_dev,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * utils/rayPooling.py:143-260  rayPooling_1cube_numpy, batched over cubes as
+ * utils/sparseCubes.py:57-62 calls it.
+ *   pred_dev     (B, D,D,D) float16 (pred_is_f16 != 0) or float32
+ *   has_thresh/thresh: selection `pred > thresh`, thresh already rounded to pred's dtype (numpy
+ *                compares a python float against a float16 array in float16); has_thresh == 0 is
+ *                prediction_thresh=None (all voxels).  Selected predictions must be > 0 (SN_ERR_DOMAIN otherwise).
+ *   viewpairs_dev (B, n_vp, 2) i32; P_dev (V,3,4) f64; xyz_dev (B,3) f32; resol_dev (B) f32
+ *   votes_out_dev (B, D,D,D) u8
+ *   workspace: sn_raypool_workspace_bytes(B, n_vp, D)
+ *   This call synchronises `stream` once at the end to read the domain-error flag.
+ */
+int64_t sn_raypool_workspace_bytes(int n_cubes, int n_vp, int D);
+int sn_raypool_votes(const void* pred_dev, int pred_is_f16, int has_thresh, float thresh, const int32_t* viewpairs_dev,
+                     const double* P_dev, int n_views, const float* xyz_dev, const float* resol_dev, int n_cubes, int n_vp,
+                     int D, uint8_t* votes_out_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* float32 -> float16 cast of the fused prediction (utils/sparseCubes.py:115) */
+int sn_cast_f32_to_f16(const float* in_dev, int64_t n, void* out_f16_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * main_reconstruct.py:132-162 -- the per-batch hot loop body as ONE call, everything resident on
+ * the device: CVC gather (+mean) -> SurfaceNet -> view-pair fusion -> float16 cast -> ray-pool votes.
+ *   outputs: fused_out_dev (B,1,D,D,D) f32, unfused_out_dev (B,n_vp,D,D,D) f32 or NULL,
+ *            pred16_out_dev (B,D,D,D) f16, votes_out_dev (B,D,D,D) u8 or NULL (skip ray pooling)
+ */
+int64_t sn_infer_batch_workspace_bytes(const sn_net* net, int n_cubes, int n_vp, int D, int mode);
+int sn_infer_batch(const sn_net* net, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
+                   int n_views, const double* P_dev, const float* xyz_dev, const float* resol_dev,
+                   const int32_t* viewpairs_dev, const float* w_dev, int n_cubes, int n_vp, int D, float min_prob_f16,
+                   float* fused_out_dev, float* unfused_out_dev, void* pred16_out_dev, uint8_t* votes_out_dev,
+                   void* workspace_dev, int64_t workspace_bytes, int mode, void* stream);
+
+/* same, HOST buffers for the per-batch arguments and results (images / cameras / weights stay
+ * resident on the device, as they are per-scene constants: main_reconstruct.py:49-51,70-72).
+ * Copies in: xyz, resol, viewpairs, w.  Copies out: fused f32, pred16, votes (each may be NULL).
+ * Synchronises `stream` before returning. */
+int sn_infer_batch_host(const sn_net* net, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
+                        int n_views, const double* P_dev, const float* xyz_host, const float* resol_host,
+                        const int32_t* viewpairs_host, const float* w_host, int n_cubes, int n_vp, int D, float min_prob_f16,
+                        float* fused_out_host, void* pred16_out_host, uint8_t* votes_out_host,
+                        void* workspace_dev, int64_t workspace_bytes, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFACENET_B200_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of libsurfacenet_b200.so (C ABI declared in include/surfacenet_b200.h).
+
+There is NO fallback: if the shared library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C surfacenet_b200/csrc``) importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsurfacenet_b200.so")
+
+SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_DOMAIN, SN_ERR_NOMEM = 0, -1, -2, -3, -4
+MODE_FP32, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "exact": MODE_TC_EXACT, "tc_exact": MODE_TC_EXACT, "fast": MODE_TC_FAST, "tc_fast": MODE_TC_FAST}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("surfacenet_b200: {} is missing -- build the CUDA library first (make -C surfacenet_b200/csrc); "
+                      "there is no CPU fallback".format(LIB_PATH))
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+# name -> (restype, argtypes); must list every symbol include/surfacenet_b200.h declares
+SIGNATURES = {
+    "sn_last_error": (C.c_char_p, []),
+    "sn_version": (_i, []),
+    "sn_launch_count": (_i64, []),
+    "sn_launch_count_reset": (None, []),
+    "sn_perspective_proj": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p]),
+    "sn_cvc_gather": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "sn_sub_channel_mean": (_i, [_p, _i64, _i, _i64, _p, _p]),
+    "sn_net_create": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i, C.POINTER(C.c_void_p)]),
+    "sn_net_destroy": (None, [_p]),
+    "sn_net_workspace_bytes": (_i64, [_p, _i, _i, _i]),
+    "sn_net_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p]),
+    "sn_net_relative_importance": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "sn_net_layer_conv": (_i, [_p, _i, _p, _i, _i, _p, _p]),
+    "sn_maxpool2": (_i, [_p, _i, _i, _i, _p, _p]),
+    "sn_net_layer_upsample": (_i, [_p, _i, _p, _i, _i, _i, _p, _i, _i, _p]),
+    "sn_fuse_weighted_average": (_i, [_p, _p, _i, _i, _i64, _p, _p]),
+    "sn_raypool_workspace_bytes": (_i64, [_i, _i, _i]),
+    "sn_raypool_votes": (_i, [_p, _i, _i, _f, _p, _p, _i, _p, _p, _i, _i, _i, _p, _p, _i64, _p]),
+    "sn_cast_f32_to_f16": (_i, [_p, _i64, _p, _p]),
+    "sn_infer_batch_workspace_bytes": (_i64, [_p, _i, _i, _i, _i]),
+    "sn_infer_batch": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i64, _i, _p]),
+    "sn_infer_batch_host": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _i64, _i, _p]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = the library does not export a declared symbol
+    _fn.restype, _fn.argtypes = _res, _args
+
+
+def last_error():
+    return lib.sn_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Map a status code to the exception the reference raises for the same condition:
+    ValueError for bad shapes / arguments (utils/rayPooling.py:201-202, utils/camera.py:163-170),
+    RuntimeError for everything the GPU runtime reports."""
+    if rc == SN_OK:
+        return
+    msg = last_error()
+    if rc in (SN_ERR_INVALID, SN_ERR_DOMAIN):
+        raise ValueError(msg)
+    raise RuntimeError("surfacenet_b200 [{}]: {}".format(rc, msg))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("surfacenet_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

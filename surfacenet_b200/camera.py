@@ -1,0 +1,36 @@
+"""Drop-in for utils/camera.py:123-184 perspectiveProj, evaluated on the GPU (sn_perspective_proj)."""
+import numpy as np
+from . import _lib
+
+
+def perspectiveProj(projection_M, xyz_3D, return_int_hw=True, return_depth=False):
+    """projection_M (3,4) / (N_Ms,3,4); xyz_3D (3,) / (N_pts,3) -> img_h, img_w[, depth], each
+    (N_pts,) / (N_Ms,N_pts); int64 when return_int_hw (round half to even), float64 otherwise."""
+    projection_M = np.asarray(projection_M)
+    xyz_3D = np.asarray(xyz_3D)
+    if projection_M.shape[-2:] != (3, 4):
+        raise ValueError("perspectiveProj needs projection_M with shape (3,4), however got {}".format(projection_M.shape))
+    if xyz_3D.ndim == 1:
+        xyz_3D = xyz_3D[None, :]
+    if xyz_3D.ndim != 2 or xyz_3D.shape[1] != 3:
+        raise ValueError("perspectiveProj needs xyz_3D with shape (3,) or (N_pts, 3), however got {}".format(xyz_3D.shape))
+    torch = _lib.require_cuda()
+    single = projection_M.ndim == 2
+    P = torch.from_numpy(np.ascontiguousarray(projection_M.reshape(-1, 3, 4), dtype=np.float64)).cuda()
+    pts = torch.from_numpy(np.ascontiguousarray(xyz_3D, dtype=np.float64)).cuda()
+    nM, nP = P.shape[0], pts.shape[0]
+    h = torch.empty((nM, nP), dtype=torch.float64, device="cuda")
+    w = torch.empty_like(h)
+    d = torch.empty_like(h) if return_depth else None
+    _lib.check(_lib.lib.sn_perspective_proj(_lib.ptr(P), nM, _lib.ptr(pts), nP, 1 if return_int_hw else 0,
+                                            _lib.ptr(h), _lib.ptr(w), _lib.ptr(d), _lib.stream_ptr()))
+    h, w = h.cpu().numpy(), w.cpu().numpy()
+    if return_int_hw:
+        with np.errstate(invalid="ignore"):
+            h, w = h.astype(np.int64), w.astype(np.int64)
+    if single:
+        h, w = h[0], w[0]
+    if return_depth:
+        d = d.cpu().numpy()
+        return h, w, (d[0] if single else d)
+    return h, w

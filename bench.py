@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SurfaceNet per-cube inference hot path (CVC gather -> 3D SurfaceNet ->
+view-pair fusion -> float16 -> ray-pool votes) on N B200s of one node.
+
+    python bench.py [--gpus N --steps K --warmup W] [--workload c3|c2|c4] [--mode fp32|exact|fast]
+    python bench.py --impl reference ...      the CPU restatement of the reference path on the host cores
+
+A "step" = one batch of the hot loop of main_reconstruct.py:132-162 per GPU.  Workload (default c3,
+BASELINE.json configs[2], the 64^3 configuration the headline target is quoted on; largest single-GPU
+config): 16 cubes of 64^3 x 5 view pairs per GPU, weighted fusion + ray pooling, DTU cal18 cameras,
+synthetic uint8 1200x1600 images, synthetic calibrated weights.  Weak scaling: every rank owns its own
+16 cubes; the per-cube fused probability (f32) and votes (u8) volumes are all-gathered ONCE at the
+end of the step, inside the timed region.
+
+value  = fused surface-probability voxels / s, whole job, inputs resident in HBM (device timed, max over ranks)
+e2e    = same metric through HotPath.infer_batch_host: pinned HOST per-batch arguments in, fused f32 +
+         float16 prediction + votes back to pinned host memory, copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FLOP_PER_PAIR_VOXEL = 1358389.0        # 2 x 679,194.5 MAC (conv + 1x1x1 layers)
+WORKLOADS = {                          # cubes per GPU, view pairs, cube side
+    "c2": dict(cubes=64, n_vp=5, D=32, name="synthetic-image DTU-camera s=32 cubes, 64 cubes x 5 view-pairs per GPU (BASELINE configs[1])"),
+    "c3": dict(cubes=16, n_vp=5, D=64, name="synthetic-image DTU-camera s=64 cubes, 16 cubes x 5 weighted view-pairs + rayPooling per GPU (BASELINE configs[2])"),
+    "c4": dict(cubes=64, n_vp=8, D=64, name="synthetic 64^3 cubes, 64 cubes x 8 view-pairs per GPU (BASELINE configs[3] = 512 cubes on 8 GPUs)"),
+}
+
+
+def unit_macs_per_voxel():
+    """MAC per full-resolution input voxel for every conv unit."""
+    from surfacenet_b200 import weights
+    res = {"conv1": 1, "side_op1": 1, "merge": 1, "conv2": 8, "side_op2": 8, "conv3": 64, "side_op3": 64, "conv4": 64, "side_op4": 64}
+    macs = []
+    for name, kind, cin, cout, k in weights.UNITS:
+        if kind == "up":
+            macs.append(0.0)
+            continue
+        key = [p for p in res if name.startswith(p)][0]
+        macs.append(cin * cout * k ** 3 / res[key])
+    return macs
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained") or d["bf16_tflops"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, bf16 sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 6] or [r for t, r in self.rows[-3:] if len(r) >= 6]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.kill()
+
+
+def make_inputs(wl, rank, n_views=49):
+    """cube origins uniform in the scan9 BB shrunk by one cube, distinct views per pair, w = rand + 0.1."""
+    import numpy as np
+    from tests import util
+    B, n_vp, D = wl["cubes"], wl["n_vp"], wl["D"]
+    rs = np.random.RandomState(100 + rank)
+    lo, hi = util.SCAN9_BB[0], util.SCAN9_BB[1] - D * 0.4
+    xyz = (lo + rs.rand(B, 3) * (hi - lo)).astype(np.float32)
+    resol = np.full(B, 0.4, np.float32)
+    pairs = np.stack([np.stack([rs.choice(n_views, 2, replace=False) for _ in range(n_vp)]) for _ in range(B)]).astype(np.int32)
+    w = (rs.rand(B, n_vp) + 0.1).astype(np.float32)
+    return pairs, xyz, resol, w
+
+
+def make_images(n_views=49, H=1200, W=1600):
+    import numpy as np
+    rs = np.random.RandomState(0)
+    return [rs.randint(0, 256, size=(H, W, 3), dtype=np.uint8) for _ in range(n_views)]
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step(wl, params, cams, imgs, sample_cubes, threads):
+    """The reference path on the host: numpy CVC + mean (utils/CVC.py), torch-CPU fp32 network + fusion
+    (nets/SurfaceNet.py restated), float16 cast + numpy ray pooling (utils/sparseCubes.py:115,57-62).
+    Returns seconds for `sample_cubes` cubes x n_vp pairs."""
+    import numpy as np
+    import torch
+    from oracle import cvc_oracle, raypool_oracle, surfacenet_oracle
+    from tests import util
+    torch.set_num_threads(threads)
+    pairs, xyz, resol, w = make_inputs(dict(wl, cubes=sample_cubes), 0)
+    t0 = time.perf_counter()
+    X = cvc_oracle.gen_coloredCubes(pairs.astype(np.int64), xyz, resol, cams, imgs, wl["D"])
+    _, X = cvc_oracle.preprocess_augmentation(None, X, util.MEAN6[None, :, None, None, None], False, False)
+    fused, _ = surfacenet_oracle.nViewPair_SurfaceNet_fn(X, params, w, N_vp=wl["n_vp"], chunk=1)
+    raypool_oracle.votes_batch(fused, pairs, xyz, resol, cams, 0.46)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    from surfacenet_b200 import weights
+    from tests import util
+    cams = util.dtu_cameras()
+    imgs = make_images()
+    params = weights.synthetic_params(0)
+    threads = os.cpu_count() or 1
+    sample = 1
+    V = wl["D"] ** 3
+    for _ in range(args.warmup):
+        cpu_reference_step(wl, params, cams, imgs, sample, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(wl, params, cams, imgs, sample, threads)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sample * V / dt
+    desc = "%d cube x %d view-pairs of %d^3 per step (CVC numpy + torch-CPU fp32 net + numpy ray pooling)" % (sample, wl["n_vp"], wl["D"])
+    print(json.dumps({
+        "impl": "reference", "metric": "fused surface-probability voxels/sec (CVC + SurfaceNet fwd + fusion + rayPooling)", "value": val,
+        "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pair_voxels_per_s": val * wl["n_vp"], "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args, wl):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from surfacenet_b200 import SurfaceNet, _lib, pipeline, weights
+    from surfacenet_b200.device import DeviceScene
+    from tests import util
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    mode = args.mode or _lib.DEFAULT_MODE
+    B, n_vp, D = wl["cubes"], wl["n_vp"], wl["D"]
+    V = D ** 3
+
+    cams = util.dtu_cameras()
+    imgs = make_images()
+    scene = DeviceScene(cams, imgs)
+    params = weights.synthetic_params(0)
+    net = SurfaceNet.Net(params)
+    hp = pipeline.HotPath(net, scene, mode=mode)
+    pairs, xyz, resol, w = make_inputs(wl, rank)
+    d_pairs, d_xyz, d_resol, d_w = (torch.from_numpy(a).to(dev) for a in (pairs, xyz, resol, w))
+    gathered_p = torch.empty((world * B, 1, D, D, D), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered_v = torch.empty((world * B, D, D, D), dtype=torch.uint8, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def gather(fused, votes):
+        if world > 1:                                                       # ONE all-gather per output at the end of the step
+            dist.all_gather_into_tensor(gathered_p, fused)
+            dist.all_gather_into_tensor(gathered_v, votes)
+
+    def step_device():
+        out = hp.infer_batch(d_pairs, d_xyz, d_resol, d_w, D, want_unfused=False, ray_pool=True)
+        gather(out["fused"], out["votes"])
+        return out
+
+    def step_host():
+        out = hp.infer_batch_host(pairs, xyz, resol, w, D, want_fused=True, ray_pool=True)
+        if world > 1:
+            gather(torch.from_numpy(out["fused"]).to(dev, non_blocking=True), torch.from_numpy(out["votes"]).to(dev, non_blocking=True))
+        return out
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn(); flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.lib.sn_launch_count_reset()
+        if profile:
+            _lib.lib.sn_profile_enable(1)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.time()
+        for a, b in evs:
+            a.record(); fn(); b.record()
+            flush.fill_(1)                                                   # L2 flush between timed steps, outside the events
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        launches = int(_lib.lib.sn_launch_count())
+        return float(t.item()) / steps, launches // steps, (t0, t1)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, launches, win = timed(step_device, args.steps, args.warmup, profile=True)
+    n_units = len(weights.UNITS)
+    ms_u = (C.c_double * n_units)(); cnt_u = (C.c_int64 * n_units)()
+    _lib.check(_lib.lib.sn_profile_collect(ms_u, cnt_u, n_units))
+    _lib.lib.sn_profile_enable(0)
+    clocks = sampler.window(*win) if sampler else None
+    ms_e2e, _, _ = timed(step_host, args.steps, max(args.warmup, 1))
+    if sampler:
+        sampler.stop()
+
+    if rank == 0:
+        tc_peak, hbm_peak, peak_src = peaks()
+        macs = unit_macs_per_voxel()
+        pair_vox_step = B * n_vp * V
+        conv_ms = sum(ms_u[i] for i in range(n_units))
+        conv_launches = sum(cnt_u[i] for i in range(n_units))
+        conv_flop_step = 2.0 * sum(macs) * pair_vox_step
+        achieved = conv_flop_step * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        per_unit = {weights.UNITS[i][0]: {"ms_per_step": ms_u[i] / args.steps, "tflops": (2.0 * macs[i] * pair_vox_step * args.steps / (ms_u[i] * 1e-3) / 1e12) if ms_u[i] > 0 else 0.0}
+                    for i in range(n_units) if cnt_u[i]}
+        fused_vox = world * B * V
+        line = {
+            "metric": "fused surface-probability voxels/sec (CVC + SurfaceNet fwd + fusion + rayPooling)",
+            "value": fused_vox / (ms_dev * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "exact": "f16x2-split operands, f32 accumulate", "tc_exact": "f16x2-split operands, f32 accumulate",
+                      "fast": "f16", "tc_fast": "f16"}[mode],
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "mode": mode, "cubes_per_gpu": B, "view_pairs": n_vp, "cube_D": D,
+                       "l2": "256 MiB flush write between timed steps; per-step activations exceed L2",
+                       "parallelism": "cube-sharded x%d, one all-gather of prob+votes per step" % world},
+            "pair_voxels_per_s": world * pair_vox_step / (ms_dev * 1e-3),
+            "path_tflops": FLOP_PER_PAIR_VOXEL * world * pair_vox_step / (ms_dev * 1e-3) / 1e12,
+            "e2e": {"value": fused_vox / (ms_e2e * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "3D conv units (%d launches/step)" % (conv_launches // args.steps), "achieved": achieved,
+                         "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src,
+                         "conv_share_of_step": conv_ms / args.steps / ms_dev, "per_unit": per_unit},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cpu_reference_step(dict(wl, D=16), params, cams, imgs, 1, threads)        # warm torch's thread pool
+            dt = cpu_reference_step(wl, params, cams, imgs, 1, threads)
+            line["cpu_baseline"] = {"value": V / dt, "unit": "voxels/s", "cores": threads, "kind": "port",
+                                    "sample": "1 cube x %d view-pairs of %d^3 (%.1f s): numpy CVC + torch-CPU fp32 net + numpy ray pooling" % (n_vp, D, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

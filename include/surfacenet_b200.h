@@ -48,6 +48,13 @@ int         sn_version(void);
 int64_t     sn_launch_count(void);
 void        sn_launch_count_reset(void);
 
+/* Per-launch timing of the convolution units with CUDA events on the launching stream (the reference
+ * has only commented-out time.time() probes: utils/rayPooling.py:69-138).  enable(1) clears and starts
+ * recording, enable(0) stops; collect() synchronises the recorded events and returns, per unit of
+ * surfacenet_b200/weights.py:UNITS (n_units must be 22), the summed device milliseconds and launch count. */
+void sn_profile_enable(int on);
+int  sn_profile_collect(double* ms_per_unit, int64_t* launches_per_unit, int n_units);
+
 /* ------------------------------------------------------------------------------------------------
  * utils/camera.py:123-184  perspectiveProj(projection_M, xyz_3D, return_int_hw, return_depth)
  *   P_dev   (n_mats,3,4) f64;  xyz_dev (n_pts,3) f64

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsurfacenet_b200.so")
 
 SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_DOMAIN, SN_ERR_NOMEM = 0, -1, -2, -3, -4
 MODE_FP32, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2
+DEFAULT_MODE = os.environ.get("SN_MODE", "fp32")      # the mode bench.py / smoke() run unless told otherwise
 MODES = {"fp32": MODE_FP32, "exact": MODE_TC_EXACT, "tc_exact": MODE_TC_EXACT, "fast": MODE_TC_FAST, "tc_fast": MODE_TC_FAST}
 
 if not os.path.exists(LIB_PATH):
@@ -25,6 +26,8 @@ SIGNATURES = {
     "sn_version": (_i, []),
     "sn_launch_count": (_i64, []),
     "sn_launch_count_reset": (None, []),
+    "sn_profile_enable": (None, [_i]),
+    "sn_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),
     "sn_perspective_proj": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p]),
     "sn_cvc_gather": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "sn_sub_channel_mean": (_i, [_p, _i64, _i, _i64, _p, _p]),

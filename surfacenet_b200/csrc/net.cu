@@ -14,6 +14,27 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- per-launch profiling (bench.py: roofline of the dominant kernel, measured live with CUDA events) ----
+struct ProfRec { int unit; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int unit, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r{unit, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+void prof_end(int unit, cudaStream_t st) {
+    if (!g_prof_on || g_prof.empty() || g_prof.back().unit != unit) return;
+    cudaEventRecord(g_prof.back().b, st);
+}
+
 static int upload(const std::vector<float>& h, float** d) {
     SN_CUDA(cudaMalloc((void**)d, std::max<size_t>(h.size(), 1) * sizeof(float)));
     SN_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -62,6 +83,23 @@ extern "C" int sn_version(void) { return 100; }
 extern "C" int64_t sn_launch_count(void) { return g_launches.load(); }
 extern "C" void sn_launch_count_reset(void) { g_launches.store(0); }
 
+extern "C" void sn_profile_enable(int on) {
+    for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+}
+extern "C" int sn_profile_collect(double* ms_per_unit, int64_t* launches_per_unit, int n_units) {
+    SN_CHECK_ARG(ms_per_unit && launches_per_unit && n_units == kNumUnits, "sn_profile_collect: expects %d units", kNumUnits);
+    for (int u = 0; u < n_units; ++u) { ms_per_unit[u] = 0; launches_per_unit[u] = 0; }
+    for (auto& r : g_prof) {
+        SN_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        SN_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_per_unit[r.unit] += ms; launches_per_unit[r.unit] += 1;
+    }
+    return SN_OK;
+}
+
 extern "C" int sn_net_create(const float* const* arrays_host, const int64_t* sizes, int n_arrays, sn_net** out) {
     SN_CHECK_ARG(arrays_host && sizes && out, "sn_net_create: NULL argument");
     SN_CHECK_ARG(n_arrays == 105, "sn_net_create: the SurfaceNet parameter list holds 105 arrays, got %d", n_arrays);
@@ -78,7 +116,7 @@ extern "C" int sn_net_create(const float* const* arrays_host, const int64_t* siz
         ConvUnit& cu = net.units[u];
         const int i0 = first_array_of_unit(u);
         const int K3 = s.K * s.K * s.K;
-        cu.kind = s.kind; cu.Cin = s.Cin; cu.Cout = s.Cout; cu.K = s.K;
+        cu.id = u; cu.kind = s.kind; cu.Cin = s.Cin; cu.Cout = s.Cout; cu.K = s.K;
         cu.dil = (s.kind == UNIT_DIL) ? 2 : 1;
         if (s.kind == UNIT_UP) {
             std::vector<float> w(arrays_host[i0], arrays_host[i0] + K3);

@@ -30,6 +30,7 @@ enum UnitId { U_CONV1_1 = 0, U_CONV1_2, U_CONV1_3, U_SIDE1, U_CONV2_1, U_CONV2_2
               U_MERGE1, U_MERGE2, U_MERGE3 };
 
 struct ConvUnit {
+    int id = -1;              // index into kUnits
     int kind, Cin, Cout, K, dil, act;
     int Cin_pad;              // Cin rounded up to CV_CI
     float* w_fp32 = nullptr;  // [ceil(Cout/16)][Cin_pad][K^3][16], zero padded
@@ -47,6 +48,10 @@ struct Net {
     float *fc1_W = nullptr, *fc1_scale = nullptr, *fc1_shift = nullptr, *lin_W = nullptr, *lin_b = nullptr;
     void* tc = nullptr;       // tensor-core side tables (conv_tc.cu), created lazily at sn_net_create
 };
+
+// per-launch CUDA-event timing of the conv units (sn_profile_enable / sn_profile_collect; bench.py roofline)
+void prof_begin(int unit, cudaStream_t st);
+void prof_end(int unit, cudaStream_t st);
 
 int conv_fp32_launch(const ConvUnit& u, const float* in, int n, int S, float* out, int C_total, int c_off, cudaStream_t st);
 int maxpool2_launch(const float* in, int n, int C, int S, float* out, cudaStream_t st);

@@ -113,6 +113,7 @@ int conv_fp32_launch(const ConvUnit& u, const float* in, int n, int S, float* ou
     const int64_t tiles = (int64_t)n * cdiv(S, CV_TD) * cdiv(S, CV_TH) * cdiv(S, CV_TW);
     SN_CHECK_ARG(tiles <= 0x7fffffff, "conv: too many tiles");
     dim3 grid((unsigned)tiles, (unsigned)cdiv(u.Cout, CV_COT));
+    prof_begin(u.id, st);
     if (u.K == 3) {
         static bool attr_set = false;
         if (!attr_set) { SN_CUDA(cudaFuncSetAttribute(conv3d_fp32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
@@ -120,6 +121,7 @@ int conv_fp32_launch(const ConvUnit& u, const float* in, int n, int S, float* ou
     } else {
         conv3d_fp32_kernel<1><<<grid, CV_THREADS, smem, st>>>(in, u.w_fp32, u.scale, u.shift, out, u.Cin, u.Cin_pad, u.Cout, S, u.dil, u.act, C_total, c_off);
     }
+    prof_end(u.id, st);
     SN_LAUNCHED();
     return SN_OK;
 }

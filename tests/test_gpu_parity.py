@@ -1,0 +1,359 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, libsurfacenet_b200.so) against the CPU
+oracle on the same seeded inputs and against the golden fixtures produced by the reference code.
+
+Bars: bit-exact for the voxel->pixel index map, the gathered colours and the ray-pool votes;
+<= 1e-4 max-abs on probabilities (BASELINE.json north_star), tolerance written at each assert.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-4          # north_star: <= 1e-4 max-abs on the surface-probability volume
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def params():
+    from surfacenet_b200 import weights
+    return weights.synthetic_params(0)
+
+
+@pytest.fixture(scope="module")
+def net(torch_cuda, params):
+    from surfacenet_b200 import SurfaceNet
+    return SurfaceNet.Net(params)
+
+
+# ---- perspectiveProj ---------------------------------------------------------------------------------
+def test_perspectiveProj_reference_doctest(torch_cuda):
+    from surfacenet_b200 import camera
+    np.random.seed(201611)                                    # utils/camera.py:144-160
+    Ms = np.random.rand(2, 3, 4)
+    pts_3D = np.random.rand(2, 3)
+    h, w = camera.perspectiveProj(Ms, pts_3D, return_int_hw=False)
+    assert np.allclose(w, np.array([[1.35860185, 0.9878389], [0.64522543, 0.76079278]]))
+    hi, wi = camera.perspectiveProj(Ms, pts_3D, return_int_hw=True)
+    assert hi.dtype == np.int64 and np.array_equal(wi, np.array([[1, 1], [1, 1]]))
+    h1, w1 = camera.perspectiveProj(Ms[1], pts_3D[0], return_int_hw=False)
+    assert np.allclose(np.r_[h1, w1], np.stack((h, w))[:, 1, 0])
+    with pytest.raises(ValueError):
+        camera.perspectiveProj(np.zeros((4, 4)), np.zeros((2, 3)))
+    with pytest.raises(ValueError):
+        camera.perspectiveProj(np.zeros((3, 4)), np.zeros((2, 2)))
+
+
+def test_perspectiveProj_golden_bit_exact(torch_cuda, golden, cams):
+    from surfacenet_b200 import camera
+    h, w, d = camera.perspectiveProj(cams[golden["pp_dtu_views"]], golden["pp_dtu_pts"], True, True)
+    assert np.array_equal(h, golden["pp_dtu_h"]) and np.array_equal(w, golden["pp_dtu_w"])
+    assert np.array_equal(d, golden["pp_dtu_depth"])           # fp64 depth, bit-exact
+
+
+# ---- CVC -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["basic", "ragged_sizes", "dup_views", "c1_s32", "outside"])
+def test_cvc_matches_reference_outputs(torch_cuda, golden, cams, name):
+    from surfacenet_b200 import CVC
+    case = util.cvc_cases(cams)[name]
+    X = CVC.gen_coloredCubes(case["pairs"], case["xyz"], case["resol"], case["cameraPOs"], case["images"], case["D"])
+    assert X.dtype == np.float32 and X.shape == golden["cvc_" + name].shape
+    assert np.array_equal(X, golden["cvc_" + name].astype(np.float32))            # exact colours
+    _, X2 = CVC.preprocess_augmentation(None, X, util.MEAN6[None, :, None, None, None], False, False)
+    assert np.array_equal(X2.reshape(-1)[::997], golden["cvc_" + name + "_pre_sample"])
+
+
+@pytest.mark.parametrize("name", ["basic", "ragged_sizes", "outside"])
+def test_cvc_index_map_bit_exact(torch_cuda, cams, name):
+    from oracle import cvc_oracle
+    from surfacenet_b200 import CVC
+    from surfacenet_b200.device import DeviceScene
+    case = util.cvc_cases(cams)[name]
+    scene = DeviceScene(case["cameraPOs"], case["images"])
+    X, iw, ih, ins = CVC.gen_coloredCubes_device(scene, case["pairs"], case["xyz"], case["resol"], case["D"], return_index=True)
+    ow, oh, oin = cvc_oracle.gen_index_map(case["pairs"], case["xyz"], case["resol"], case["cameraPOs"], case["images"], case["D"])
+    assert iw.dtype == torch_cuda.int32
+    assert np.array_equal(iw.cpu().numpy(), ow), "w index map differs"
+    assert np.array_equal(ih.cpu().numpy(), oh), "h index map differs"
+    assert np.array_equal(ins.cpu().numpy().astype(bool), oin)
+
+
+def test_cvc_full_size_s64_index_and_colour(torch_cuda, cams):
+    """BASELINE full size (s=64): compare with the oracle on 2 cubes x 5 pairs (oracle ~2 s)."""
+    from oracle import cvc_oracle
+    from surfacenet_b200 import CVC
+    rs = np.random.RandomState(7)
+    used = list(range(0, 49, 4))
+    imgs = util.image_list(49, used)
+    pairs = rs.choice(used, size=(2, 5, 2))
+    xyz = np.array([[10.0, -30.0, 620.0], [30.0, 0.0, 650.0]], np.float32)
+    resol = np.full(2, 0.4, np.float32)
+    X = CVC.gen_coloredCubes(pairs, xyz, resol, cams, imgs, 64)
+    Xo = cvc_oracle.gen_coloredCubes(pairs, xyz, resol, cams, imgs, 64)
+    assert np.array_equal(X, Xo)
+
+
+def test_cvc_errors(torch_cuda, cams):
+    from surfacenet_b200 import CVC
+    imgs = util.image_list(49, [0, 1])
+    with pytest.raises(ValueError):
+        CVC.gen_coloredCubes(np.zeros((1, 2), np.int64), np.zeros((1, 3), np.float32), np.ones(1, np.float32), cams, imgs, 8)
+    with pytest.raises(ValueError):     # view without an image
+        CVC.gen_coloredCubes(np.array([[[0, 7]]]), np.zeros((1, 3), np.float32), np.ones(1, np.float32), cams, imgs, 8)
+    out = CVC.gen_coloredCubes(np.zeros((0, 1, 2), np.int64), np.zeros((0, 3), np.float32), np.ones(0, np.float32), cams, imgs, 8)
+    assert out.shape == (0, 6, 8, 8, 8)
+
+
+# ---- ray pooling ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sheet16", "sheet32_dup", "ties", "lowres_collide", "all_ones", "empty",
+                                  "none_thresh_f32", "exact_thresh"])
+def test_raypool_matches_reference_outputs(torch_cuda, golden, cams, name):
+    from surfacenet_b200 import rayPooling
+    case = util.raypool_cases(cams)[name]
+    votes = rayPooling.rayPooling_1cube_numpy(case["cameraPOs"], None, case["pred"], case["pairs"], case["xyz"],
+                                              case["resol"], prediction_thresh=case["thresh"])
+    assert votes.dtype == np.int64
+    assert np.array_equal(votes.astype(np.uint8), golden["rp_" + name])
+
+
+def test_raypool_s64_batched_vs_oracle(torch_cuda, cams):
+    """Full-size cubes, batched call, 5 pairs with a duplicated view: exact vote equality."""
+    import torch
+    from oracle import raypool_oracle
+    from surfacenet_b200 import rayPooling
+    preds = np.stack([util.sheet_prediction(64, 0.3 * i, 0.06) for i in range(3)])
+    pairs = np.array([[[0, 5], [17, 22], [5, 30], [40, 41], [8, 9]],
+                      [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10]],
+                      [[12, 12], [12, 13], [20, 44], [45, 46], [47, 48]]], np.int32)
+    xyz = np.array([[20.0, -12.5, 630.0], [-10.3, 30.7, 655.1], [55.25, -60.0, 600.5]], np.float32)
+    resol = np.full(3, 0.4, np.float32)
+    votes = rayPooling.votes_device(torch.from_numpy(preds).cuda(), torch.from_numpy(pairs).cuda(), torch.from_numpy(xyz).cuda(),
+                                    torch.from_numpy(resol).cuda(), torch.from_numpy(cams).cuda(), cams.shape[0], 0.46).cpu().numpy()
+    for b in range(3):
+        ref = raypool_oracle.rayPooling_1cube_numpy(cams, None, preds[b], pairs[b], xyz[b], resol[b], prediction_thresh=0.46)
+        assert np.array_equal(votes[b], ref.astype(np.uint8)), "cube %d votes differ" % b
+    assert votes.max() <= 10 and votes.max() >= 2
+
+
+def test_raypool_errors(torch_cuda, cams):
+    from surfacenet_b200 import rayPooling
+    with pytest.raises(ValueError):
+        rayPooling.rayPooling_1cube_numpy(cams, None, np.zeros((2, 2, 4, 4, 4)), np.array([[0, 1]]), np.zeros(3, np.float32), np.float32(1))
+    with pytest.raises(ValueError):     # domain: selected predictions must be > 0
+        rayPooling.rayPooling_1cube_numpy(cams, None, np.zeros((4, 4, 4), np.float32), np.array([[0, 1]]), np.zeros(3, np.float32),
+                                          np.float32(1), prediction_thresh=None)
+
+
+# ---- network: single layers ----------------------------------------------------------------------------
+def _layer_in(rs, n, C, S):
+    return (rs.standard_normal((n, C, S, S, S)) * 1.5).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,S", [("conv1_1", 12), ("conv1_2", 9), ("side_op1", 8), ("conv2_1", 8), ("conv3_2", 6),
+                                    ("conv4_1", 7), ("conv4_2", 8), ("side_op4", 5), ("merge_conv", 8), ("merge_conv2", 8),
+                                    ("merge_conv3", 8)])
+def test_conv_units_fp32(torch_cuda, net, params, name, S):
+    """conv + BatchNorm + activation units, odd sizes included (tile edges), vs torch-CPU fp32."""
+    import ctypes
+    import torch
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import _lib, weights
+    names = [u[0] for u in weights.UNITS]
+    u = names.index(name)
+    _, kind, cin, cout, k = weights.UNITS[u]
+    rs = np.random.RandomState(u)
+    x = _layer_in(rs, 2, cin, S)
+    act = "sigmoid" if name in weights.SIGMOID_UNITS else "relu"
+    with torch.no_grad():
+        ref = so.conv_bn(torch.from_numpy(x), params, weights.unit_index()[name], act, dilated=(kind == "dil")).numpy()
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty((2, cout, S, S, S), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_net_layer_conv(net.handle, u, _lib.ptr(xd), 2, S, _lib.ptr(out), _lib.stream_ptr()))
+    err = np.abs(out.cpu().numpy() - ref).max()
+    scale = max(1.0, np.abs(ref).max())
+    assert err <= 2e-5 * scale, "%s: max-abs %g" % (name, err)          # fp32 accumulation-order noise only
+
+
+@pytest.mark.parametrize("unit,f,S", [("up2", 2, 5), ("up3", 4, 3), ("up4", 4, 4)])
+def test_upsample_units(torch_cuda, net, params, unit, f, S):
+    import torch
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import _lib, weights
+    names = [u[0] for u in weights.UNITS]
+    u = names.index(unit)
+    rs = np.random.RandomState(3)
+    x = rs.rand(2, 16, S, S, S).astype(np.float32)
+    ref = so.upsample(torch.from_numpy(x), params[weights.unit_index()[unit]], f).numpy()
+    out = torch.zeros((2, 64, S * f, S * f, S * f), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_net_layer_upsample(net.handle, u, _lib.ptr(torch.from_numpy(x).cuda()), 2, 16, S, _lib.ptr(out), 64, 32,
+                                              _lib.stream_ptr()))
+    o = out.cpu().numpy()
+    assert np.abs(o[:, 32:48] - ref).max() <= 1e-6
+    assert o[:, :32].max() == 0 and o[:, 48:].max() == 0
+
+
+def test_upsample_micro_cases_device(torch_cuda, net):
+    """[1,2] -> x4 [1, 2/3, 1, 4/3, 2, 4/3, 2/3, 0];  x2 [1, 1.5, 2, 1]."""
+    import torch
+    from surfacenet_b200 import _lib, weights
+    names = [u[0] for u in weights.UNITS]
+    x = torch.zeros(1, 1, 2, 2, 2); x[0, 0, :, 0, 0] = torch.tensor([1.0, 2.0])
+    for unit, f, want in (("up3", 4, [1, 2 / 3, 1.0, 4 / 3, 2, 4 / 3, 2 / 3, 0]), ("up2", 2, [1, 1.5, 2, 1.0])):
+        out = torch.zeros((1, 1, 2 * f, 2 * f, 2 * f), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib.sn_net_layer_upsample(net.handle, names.index(unit), _lib.ptr(x.cuda()), 1, 1, 2, _lib.ptr(out), 1, 0,
+                                                  _lib.stream_ptr()))
+        assert np.allclose(out[0, 0, :, 0, 0].cpu().numpy(), want, atol=1e-6)
+
+
+def test_maxpool_and_fusion(torch_cuda):
+    import torch
+    import torch.nn.functional as F
+    from surfacenet_b200 import _lib
+    rs = np.random.RandomState(0)
+    x = torch.from_numpy(rs.standard_normal((2, 5, 6, 6, 6)).astype(np.float32))
+    out = torch.empty((2, 5, 3, 3, 3), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_maxpool2(_lib.ptr(x.cuda()), 2, 5, 6, _lib.ptr(out), _lib.stream_ptr()))
+    assert torch.equal(out.cpu(), F.max_pool3d(x, 2, 2))
+    p = torch.from_numpy(rs.rand(3, 4, 100).astype(np.float32))
+    w = torch.from_numpy((rs.rand(3, 4) + 0.1).astype(np.float32))
+    fo = torch.empty((3, 100), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_fuse_weighted_average(_lib.ptr(p.cuda()), _lib.ptr(w.cuda()), 3, 4, 100, _lib.ptr(fo), _lib.stream_ptr()))
+    ref = (p * (w / w.sum(1, keepdim=True))[:, :, None]).sum(1)
+    assert (fo.cpu() - ref).abs().max() <= 1e-6
+
+
+# ---- network: whole forward -----------------------------------------------------------------------------
+def _real_like_X(cams, D, n_cubes=2, n_vp=2, seed=0):
+    from oracle import cvc_oracle
+    rs = np.random.RandomState(seed)
+    used = [8, 9, 22, 23, 30, 33]
+    imgs = util.image_list(49, used)
+    pairs = rs.choice(used, size=(n_cubes, n_vp, 2))
+    xyz = (np.array([10.0, -30.0, 620.0]) + rs.rand(n_cubes, 3) * 20).astype(np.float32)
+    resol = np.full(n_cubes, 0.4, np.float32)
+    X = cvc_oracle.gen_coloredCubes(pairs, xyz, resol, cams, imgs, D)
+    _, X = cvc_oracle.preprocess_augmentation(None, X, util.MEAN6[None, :, None, None, None], False, False)
+    return X, pairs, xyz, resol, imgs
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+def test_forward_s32_two_pairs(torch_cuda, params, cams, mode):
+    """Whole network + weighted fusion on CVC input, s=32, 2 cubes x 2 pairs vs the torch-CPU fp32 oracle."""
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet
+    X, *_ = _real_like_X(cams, 32)
+    w = np.array([[0.7, 0.2], [0.3, 0.9]], np.float32)
+    fused_o, unf_o = so.nViewPair_SurfaceNet_fn(X, params, w, N_vp=2)
+    _, fn = SurfaceNet.SurfaceNet_inference(2, params, ["output_SurfaceNet_reshape", "output_softmaxWeights"], mode=mode)
+    fused, unf = fn(X, w)
+    assert fused.shape == (2, 1, 32, 32, 32) and unf.shape == (2, 2, 32, 32, 32) and fused.dtype == np.float32
+    e_f, e_u = np.abs(fused - fused_o).max(), np.abs(unf - unf_o).max()
+    print("mode %s: max-abs fused %.3g unfused %.3g; prob mean %.3f frac>0.46 %.3f" % (mode, e_f, e_u, fused_o.mean(), (fused_o > 0.46).mean()))
+    assert e_f <= PROB_TOL and e_u <= PROB_TOL
+    assert 0.05 < (fused_o > 0.46).mean() < 0.95            # the synthetic weights give a spread output
+
+
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+def test_forward_single_pair_and_odd_batch(torch_cuda, params, cams, mode):
+    """N_vp == 1: fused and unfused are the same tensor (SurfaceNet.py:354-357); s=16, 3 cubes."""
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet
+    X, *_ = _real_like_X(cams, 16, n_cubes=3, n_vp=1, seed=2)
+    o, _ = so.nViewPair_SurfaceNet_fn(X, params, None, N_vp=1)
+    _, fn = SurfaceNet.SurfaceNet_inference(1, params, mode=mode)
+    fused, unf = fn(X)
+    assert fused.shape == (3, 1, 16, 16, 16) and unf is fused
+    assert np.abs(fused - o).max() <= PROB_TOL
+
+
+def test_forward_fast_mode_reports_error(torch_cuda, params, cams):
+    """Single-pass fp16 operands: explicitly NOT a parity mode; its error is measured and bounded loosely."""
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet
+    X, *_ = _real_like_X(cams, 32, n_cubes=1, n_vp=2, seed=4)
+    w = np.array([[0.5, 0.5]], np.float32)
+    fused_o, _ = so.nViewPair_SurfaceNet_fn(X, params, w, N_vp=2)
+    _, fn = SurfaceNet.SurfaceNet_inference(2, params, mode="fast")
+    fused, _ = fn(X, w)
+    err = np.abs(fused - fused_o).max()
+    print("fast mode max-abs %.3g" % err)
+    assert err <= 5e-2
+
+
+def test_forward_errors(torch_cuda, params):
+    from surfacenet_b200 import SurfaceNet
+    _, fn = SurfaceNet.SurfaceNet_inference(2, params)
+    with pytest.raises(TypeError):
+        fn(np.zeros((2, 6, 8, 8, 8), np.float32))
+    with pytest.raises(ValueError):
+        fn(np.zeros((3, 6, 8, 8, 8), np.float32), np.ones((1, 2), np.float32))
+    with pytest.raises(ValueError):
+        fn(np.zeros((2, 5, 8, 8, 8), np.float32), np.ones((1, 2), np.float32))
+    with pytest.raises(ValueError):     # two 2^3 poolings need D % 4 == 0
+        fn(np.zeros((2, 6, 6, 6, 6), np.float32), np.ones((1, 2), np.float32))
+    with pytest.raises(ValueError):
+        SurfaceNet.Net(params[:50])
+
+
+def test_relative_importance(torch_cuda, params):
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet
+    rs = np.random.RandomState(9)
+    f = rs.standard_normal((4 * 6, 258)).astype(np.float32)
+    imp_fn, _ = SurfaceNet.SurfaceNet_inference(2, params)
+    out = imp_fn(f, n_samples_perGroup=6)
+    ref = so.viewPair_relativeImpt_fn(f, params, 6)
+    assert out.shape == (4, 6) and np.abs(out - ref).max() <= 1e-5
+    assert np.allclose(out.sum(1), 1, atol=1e-5)
+    with pytest.raises(ValueError):
+        imp_fn(f, n_samples_perGroup=5)
+
+
+# ---- the fused hot loop body ----------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["fp32", "exact"])
+def test_infer_batch_host_matches_oracle_pipeline(torch_cuda, params, cams, mode):
+    """main_reconstruct.py:134-162 as one call with host buffers: CVC -> net -> fusion -> f16 -> votes."""
+    from oracle import cvc_oracle, raypool_oracle, surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet, pipeline
+    from surfacenet_b200.device import DeviceScene
+    D = 32
+    X, pairs, xyz, resol, imgs = _real_like_X(cams, D, n_cubes=2, n_vp=3, seed=5)
+    w = (np.random.RandomState(3).rand(2, 3) + 0.1).astype(np.float32)
+    fused_o, _ = so.nViewPair_SurfaceNet_fn(X, params, w, N_vp=3)
+    net = SurfaceNet.Net(params)
+    hp = pipeline.HotPath(net, DeviceScene(cams, imgs), mode=mode)
+    out = hp.infer_batch_host(pairs, xyz, resol, w, D)
+    assert np.abs(out["fused"] - fused_o).max() <= PROB_TOL
+    # votes: bit-exact against the oracle run on the DEVICE's own float16 prediction (a 1e-5 difference in the
+    # probability may legitimately flip a float16 rounding; the vote logic itself must be exact)
+    p16 = out["pred16"]
+    assert p16.dtype == np.float16 and np.array_equal(p16, out["fused"][:, 0].astype(np.float16))
+    for b in range(2):
+        ref = raypool_oracle.rayPooling_1cube_numpy(cams, None, p16[b], pairs[b], xyz[b], resol[b], prediction_thresh=0.46)
+        assert np.array_equal(out["votes"][b], ref.astype(np.uint8))
+    assert out["votes"].max() >= 1
+    assert hp.h2d_bytes > 0 and hp.d2h_bytes == 2 * D ** 3 * 7
+
+
+def test_infer_batch_device_equals_host_entry(torch_cuda, params, cams):
+    import torch
+    from surfacenet_b200 import SurfaceNet, pipeline
+    from surfacenet_b200.device import DeviceScene
+    D = 16
+    _, pairs, xyz, resol, imgs = _real_like_X(cams, D, n_cubes=3, n_vp=2, seed=6)
+    w = (np.random.RandomState(4).rand(3, 2) + 0.1).astype(np.float32)
+    hp = pipeline.HotPath(SurfaceNet.Net(params), DeviceScene(cams, imgs))
+    h = hp.infer_batch_host(pairs, xyz, resol, w, D)
+    d = hp.infer_batch(torch.from_numpy(pairs.astype(np.int32)).cuda(), torch.from_numpy(xyz).cuda(), torch.from_numpy(resol).cuda(),
+                       torch.from_numpy(w).cuda(), D, want_unfused=True)
+    assert np.array_equal(d["fused"].cpu().numpy(), h["fused"]) and np.array_equal(d["votes"].cpu().numpy(), h["votes"])
+    assert d["unfused"].shape == (3, 2, D, D, D)
+    empty = hp.infer_batch_host(pairs[:0], xyz[:0], resol[:0], w[:0], D)
+    assert empty["fused"].shape == (0, 1, D, D, D)

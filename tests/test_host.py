@@ -1,0 +1,154 @@
+"""CPU-only tests of the host logic: the C ABI library loads and exports every symbol the header
+declares (no compute calls), the parameter-list layout, cube sharding (gloo, world_size 2), and that
+the product path refuses to run without a GPU instead of falling back."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import util
+
+REPO = util.REPO
+
+
+def _declared_symbols():
+    src = open(os.path.join(REPO, "include", "surfacenet_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    lib_path = os.path.join(REPO, "surfacenet_b200", "libsurfacenet_b200.so")
+    if not os.path.exists(lib_path):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(lib_path)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libsurfacenet_b200.so does not export " + n
+    from surfacenet_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == names, "ctypes binding and header disagree"
+    assert _lib.lib.sn_version() >= 100
+    assert _lib.lib.sn_raypool_workspace_bytes(2, 5, 64) > 0         # pure host arithmetic, no GPU needed
+    assert _lib.lib.sn_raypool_workspace_bytes(-1, 5, 64) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from surfacenet_b200 import CVC, SurfaceNet, rayPooling, weights
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SurfaceNet.SurfaceNet_inference(1, weights.synthetic_params(0))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rayPooling.rayPooling_1cube_numpy(util.dtu_cameras(), None, np.ones((4, 4, 4), np.float16), np.array([[0, 1]]),
+                                          np.zeros(3, np.float32), np.float32(0.4), 0.46)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CVC.gen_coloredCubes(np.array([[[0, 1]]]), np.zeros((1, 3), np.float32), np.ones(1, np.float32), util.dtu_cameras(),
+                             util.image_list(49, [0, 1]), 8)
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "surfacenet_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f + " imports the oracle"
+
+
+def test_parameter_layout():
+    from surfacenet_b200 import weights
+    shapes = weights.expected_shapes()
+    assert len(shapes) == 105
+    idx = weights.unit_index()
+    assert idx["up2"] == 40 and idx["up3"] == 61 and idx["up4"] == 82 and idx["merge_conv"] == 83 and idx["fc1_W"] == 98   # App. B
+    assert shapes[idx["conv4_1"]] == (160, 300, 3, 3, 3) and shapes[idx["side_op4"]] == (300, 16, 1, 1, 1)               # (C_in, C_out, ...)
+    assert sum(int(np.prod(s)) for i, s in enumerate(shapes) if len(s) == 5 and s[0] != 1 or i == idx["merge_conv3"]) == 8811252
+    p = weights.synthetic_params(0)
+    assert np.array_equal(p[40], weights.upsample_W(3)) and np.allclose(weights.upsample_W(5)[0, 0, :, 2, 2], [1 / 3, 2 / 3, 1, 2 / 3, 1 / 3])
+    with pytest.raises(ValueError):
+        weights.validate(p[:-1])
+    bad = list(p); bad[0] = bad[0][:, :5]
+    with pytest.raises(ValueError):
+        weights.validate(bad)
+    p2 = weights.synthetic_params(0)
+    assert all(np.array_equal(a, b) for a, b in zip(p, p2))
+
+
+def test_model_file_roundtrip(tmp_path):
+    import pickle
+    from surfacenet_b200 import weights
+    p = weights.synthetic_params(0, calibrated=False)
+    f = tmp_path / "x.model"
+    with open(f, "wb") as fh:
+        pickle.dump(p, fh, protocol=2)                    # the reference writes py2 pickles (SurfaceNet.py:397-399)
+    q = weights.load_model_file(str(f))
+    assert all(np.array_equal(a, b) for a, b in zip(p, q))
+    np.savez(tmp_path / "x.npz", **{str(i): a for i, a in enumerate(p)})
+    q = weights.load_model_file(str(tmp_path / "x.npz"))
+    assert all(np.array_equal(a, b) for a, b in zip(p, q))
+
+
+def test_shard_bounds():
+    from surfacenet_b200 import pipeline
+    assert pipeline.shard_bounds(512, 8) == (64, [(64 * r, 64 * r + 64) for r in range(8)])
+    per, b = pipeline.shard_bounds(10, 4)
+    assert per == 3 and b == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    per, b = pipeline.shard_bounds(2, 4)
+    assert per == 1 and b == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert pipeline.shard_bounds(0, 2) == (0, [(0, 0), (0, 0)])
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {repo!r})
+import numpy as np, torch, torch.distributed as dist
+from surfacenet_b200 import pipeline
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+n = {n}
+full_p = torch.arange(n * 8, dtype=torch.float32).reshape(n, 2, 2, 2)
+full_v = (torch.arange(n * 8) % 251).to(torch.uint8).reshape(n, 2, 2, 2)
+calls = []
+def compute(lo, hi):
+    calls.append((lo, hi))
+    return full_p[lo:hi] * 2, full_v[lo:hi]
+p, v = pipeline.infer_sharded(compute, n, [((2, 2, 2), torch.float32), ((2, 2, 2), torch.uint8)], rank, world, device="cpu")
+assert torch.equal(p, full_p * 2) and torch.equal(v, full_v), "rank %d reassembly wrong" % rank
+per, bounds = pipeline.shard_bounds(n, world)
+assert calls == ([bounds[rank]] if bounds[rank][1] > bounds[rank][0] else [])
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+@pytest.mark.parametrize("n", [5, 1])
+def test_infer_sharded_gloo_world2(tmp_path, n):
+    """cube-sharded batch + one all-gather per output, world_size 2 over gloo (ragged and nearly empty shards)."""
+    port = 29600 + os.getpid() % 200 + n
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(repo=REPO, port=port, n=n))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "OK %d" % r in o, o[-2000:]
+
+
+def test_bench_reference_arm_json():
+    """--impl reference prints one JSON line with the contract keys (tiny workload for speed)."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "c2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "voxels/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0

@@ -116,8 +116,8 @@ int sn_net_relative_importance(const sn_net* net, const float* features_dev, int
 
 /* single layers, exposed for per-kernel parity tests and calibration (NCDHW fp32):
  *   conv + BatchNorm(inference) + activation: nets/SurfaceNet.py:33-74 units; `unit` indexes
- *   surfacenet_b200/weights.py:UNITS.  in (n,C_in,S,S,S) -> out (n,C_out,S,S,S). */
-int sn_net_layer_conv(const sn_net* net, int unit, const float* in_dev, int n, int S, float* out_dev, void* stream);
+ *   surfacenet_b200/weights.py:UNITS.  in (n,C_in,S,S,S) -> out (n,C_out,S,S,S); mode = SN_MODE_*. */
+int sn_net_layer_conv(const sn_net* net, int unit, const float* in_dev, int n, int S, float* out_dev, int mode, void* stream);
 int sn_maxpool2(const float* in_dev, int n, int C, int S, float* out_dev, void* stream);      /* SurfaceNet.py:37,46 */
 /* nets/layers.py:376-390: zero-stuff by f, k^3 fixed conv (W from the parameter list), 'same'.
  *   in (n,C,S,S,S) -> written into out (n, C_total, fS,fS,fS) at channel offset c_off. */

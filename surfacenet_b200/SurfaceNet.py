@@ -31,7 +31,7 @@ class Net:
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
-        if h:
+        if h and _lib is not None and getattr(_lib, "lib", None) is not None:      # interpreter shutdown clears module globals
             _lib.lib.sn_net_destroy(h)
 
     def workspace(self, nbytes):

@@ -36,7 +36,7 @@ SIGNATURES = {
     "sn_net_workspace_bytes": (_i64, [_p, _i, _i, _i]),
     "sn_net_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i64, _i, _p]),
     "sn_net_relative_importance": (_i, [_p, _p, _i64, _i, _p, _p]),
-    "sn_net_layer_conv": (_i, [_p, _i, _p, _i, _i, _p, _p]),
+    "sn_net_layer_conv": (_i, [_p, _i, _p, _i, _i, _p, _i, _p]),
     "sn_maxpool2": (_i, [_p, _i, _i, _i, _p, _p]),
     "sn_net_layer_upsample": (_i, [_p, _i, _p, _i, _i, _i, _p, _i, _i, _p]),
     "sn_fuse_weighted_average": (_i, [_p, _p, _i, _i, _i64, _p, _p]),

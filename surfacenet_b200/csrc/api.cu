@@ -76,9 +76,9 @@ extern "C" int sn_infer_batch_host(const sn_net* h, const uint8_t* images_dev, c
                                    const int32_t* viewpairs_host, const float* w_host, int n_cubes, int n_vp, int D, float min_prob_f16,
                                    float* fused_out_host, void* pred16_out_host, uint8_t* votes_out_host,
                                    void* workspace_dev, int64_t workspace_bytes, int mode, void* stream) {
-    SN_CHECK_ARG(xyz_host && resol_host && viewpairs_host, "sn_infer_batch_host: NULL argument");
     SN_CHECK_ARG(n_cubes >= 0 && n_vp >= 1 && D >= 4, "sn_infer_batch_host: bad sizes");
     if (n_cubes == 0) return SN_OK;
+    SN_CHECK_ARG(xyz_host && resol_host && viewpairs_host, "sn_infer_batch_host: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t V = (int64_t)D * D * D;
     // carve the staging buffers off the tail of the workspace

@@ -1,19 +1,706 @@
-// Tensor-core (tcgen05) convolution path -- placeholder wiring until the kernels land.
+// K2/K3 -- tensor-core (tcgen05 + TMEM + TMA) implicit-GEMM 3D convolution units of SurfaceNet
+// (nets/SurfaceNet.py:33-74; dilated units nets/layers.py:200-253) and the forward graph built on them.
+//
+// Data layout ("blk"): activations live in HBM as fp16 channel-blocked planes
+//     act[n][prec][cg][d][h][w][8]      prec: 0 = hi = fp16(x), 1 = lo = fp16(x - hi) (SN_MODE_TC_EXACT only)
+// so that (a) one 4-D TMA box {8*PW, HH, HD, 2 groups} drops a zero-padded halo tile of 16 channels into
+// shared memory exactly in the tcgen05 K-major / no-swizzle canonical layout (core matrix = 8 voxels along
+// w x 8 channels = 128 contiguous bytes; LBO = one channel-group plane, SBO = one padded row), and
+// (b) every 3x3x3 / dilated tap is just a different START ADDRESS of the same tile: the A operand of
+// tap (kd,kh,kw) for the accumulator of plane a is base + (((a+kd*dil)*HH + kh*dil)*PW + kw*dil)*16 B.
+// No im2col copy is ever materialised; each input voxel is read from L2 ~2x per layer instead of 27x.
+//
+// One CTA owns AD accumulators in TMEM (each M = 128 voxels = 16 rows (h) x 8 (w) of one d-plane,
+// N = N_tile output channels, fp32), loops over 16-channel blocks (A ring, 2 stages) and taps (B = weight
+// ring, NB stages, 1-D bulk copies of pre-arranged canonical tiles) and issues, per (block, tap, plane),
+//   exact: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (fp16 2-term split of both operands; fp32 accumulate)
+//   fast : A_hi*W_hi
+// Warp roles: 0 = A producer (TMA), 1 = B producer (bulk copy), 2 = MMA issuer, 3 = TMEM allocator,
+// 4..7 = epilogue (TMEM -> registers -> folded BatchNorm + ReLU/sigmoid -> hi/lo split -> blk store, or the
+// fused merge_conv3 1x1x1 + sigmoid -> fp32 probability).
 #include "net.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <math.h>
 
 namespace sn {
 
-int tc_prepare(Net& net) { (void)net; return SN_OK; }
-void tc_destroy(Net& net) { (void)net; }
-int64_t tc_workspace_bytes(const Net& net, int n_pc, int D, int mode) {
-    (void)net; (void)n_pc; (void)D; (void)mode;
-    set_error("tensor-core modes are not available in this build");
-    return -1;
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 "version 1"):
+//   bits [0,14) start >> 4, [16,30) leading (K-direction core-matrix) byte offset >> 4,
+//   [32,46) stride (M/N-direction 8-row group) byte offset >> 4, [46,48) version = 1, [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 256;
+constexpr int TC_TW = 8, TC_TH = 16;          // one accumulator = 16 rows (h) x 8 voxels (w) of one d-plane
+constexpr int EPI_BLK = 0, EPI_FINAL = 1;
+
+struct ConvTcParams {
+    int S, n_pc, dil, K, taps, n_cblk, cg_in, P, AD, NB;
+    int PW, HH, HD;                 // halo tile extents (voxels)
+    int a_prec_bytes;               // bytes of one precision plane of one A stage = PW*HH*HD*32
+    int tiles_w, tiles_h, tiles_d;
+    int n_ntiles, nt_size[2], nt_off[2];
+    long long nt_woff[2];           // byte offset of the N-tile's weights
+    const unsigned char* weights;   // [ntile][cblk][tap][prec][kg 2][N/8][8 n][8 k] fp16
+    const float* scale;             // folded BatchNorm (x 2^-k of the weight pre-scaling), zero for padded channels
+    const float* shift;
+    int act, epi;
+    // EPI_BLK
+    __half* out; int cg_out_total, cg_out_off;
+    // EPI_FINAL: fused merge_conv3 (1x1x1, C -> 1) + BatchNorm + sigmoid      SurfaceNet.py:74
+    const float* w3; float scale3, shift3; int c3; float* prob_out;
+};
+
+__device__ __forceinline__ float tc_act(float y, int act) {
+    if (act == SN_ACT_RELU) return fmaxf(y, 0.f);
+    if (act == SN_ACT_SIGMOID) return 1.f / (1.f + expf(-y));
+    return y;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = p.P, AD = p.AD, NB = p.NB;
+    const int nt = blockIdx.y;
+    const int N = p.nt_size[nt];
+    const uint32_t a_stage_bytes = (uint32_t)p.a_prec_bytes * P;
+    const uint32_t b_prec_bytes = (uint32_t)N * 32;
+    const uint32_t b_stage_bytes = b_prec_bytes * P;
+    unsigned char* smA = smem;                                        // [2][P][2 groups][HD][HH][PW][8] fp16
+    unsigned char* smB = smem + 2 * a_stage_bytes;                    // [NB][P][2][N/8][8][8] fp16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)NB * b_stage_bytes);
+    uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + NB, *acc_full = bars + 4 + 2 * NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NB);
+
+    // tile -> (pair-cube, d0, h0, w0)
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int td = t % p.tiles_d; t /= p.tiles_d;
+    const int pc = t;
+    const int w0 = tw * TC_TW, h0 = th * TC_TH, d0 = td * AD;
+    const int pad = p.dil * (p.K / 2);
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < AD * N) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== A producer: one zero-padded halo tile of 16 channels (x P precisions) per channel block =====
+        if (lane == 0) {
+            for (int cb = 0; cb < p.n_cblk; ++cb) {
+                const int s = cb & 1;
+                mbar_wait(&a_empty[s], ((cb >> 1) & 1) ^ 1);
+                mbar_expect_tx(&a_full[s], a_stage_bytes);
+                for (int pr = 0; pr < P; ++pr)
+                    tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
+                                8 * (w0 - pad), h0 - pad, d0 - pad, (pc * P + pr) * p.cg_in + 2 * cb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== B producer: the (channel block, tap) weight tile, already in canonical layout in HBM =====
+        if (lane == 0) {
+            const unsigned char* wsrc = p.weights + p.nt_woff[nt];
+            const int total = p.n_cblk * p.taps;
+            for (int it = 0; it < total; ++it) {
+                const int s = it % NB;
+                mbar_wait(&b_empty[s], ((it / NB) & 1) ^ 1);
+                mbar_expect_tx(&b_full[s], b_stage_bytes);
+                bulk_load(smB + (size_t)s * b_stage_bytes, wsrc + (size_t)it * b_stage_bytes, b_stage_bytes, &b_full[s]);
+            }
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, N, M=128
+            const uint32_t lbo_a = (uint32_t)p.a_prec_bytes / 2, sbo_a = (uint32_t)p.PW * 16;
+            const uint32_t lbo_b = (uint32_t)N * 16, sbo_b = 128;
+            const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
+            int it = 0;
+            for (int cb = 0; cb < p.n_cblk; ++cb) {
+                const int sa = cb & 1;
+                mbar_wait(&a_full[sa], (cb >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smA_u + sa * a_stage_bytes, a_lo = a_hi + p.a_prec_bytes;
+                for (int tap = 0; tap < p.taps; ++tap, ++it) {
+                    const int sb = it % NB;
+                    mbar_wait(&b_full[sb], (it / NB) & 1);
+                    tc_fence_after();
+                    const int kw = tap % p.K, kh = (tap / p.K) % p.K, kd = tap / (p.K * p.K);
+                    const uint32_t b_hi = smB_u + sb * b_stage_bytes;
+                    const uint64_t db_hi = make_desc(b_hi, lbo_b, sbo_b);
+                    const uint64_t db_lo = make_desc(b_hi + b_prec_bytes, lbo_b, sbo_b);
+                    const uint32_t first = (it == 0) ? 0u : 1u;
+                    for (int a = 0; a < AD; ++a) {
+                        const uint32_t off = (uint32_t)((((a + kd * p.dil) * p.HH + kh * p.dil) * p.PW + kw * p.dil) * 16);
+                        const uint32_t dcol = tmem_base + (uint32_t)(a * N);
+                        const uint64_t da_hi = make_desc(a_hi + off, lbo_a, sbo_a);
+                        tc_mma(dcol, da_hi, db_hi, idesc, first);
+                        if (P == 2) {
+                            const uint64_t da_lo = make_desc(a_lo + off, lbo_a, sbo_a);
+                            tc_mma(dcol, da_lo, db_hi, idesc, 1u);
+                            tc_mma(dcol, da_hi, db_lo, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&b_empty[sb]);              // weight stage free once these MMAs retire
+                }
+                tc_commit(&a_empty[sa]);
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM lane quarter (warp % 4) -> rows m = 32 q + lane -> voxel (h0 + m/8, w0 + m%8) =====
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int h = h0 + (m >> 3), w = w0 + (m & 7);
+        const int S = p.S;
+        const long long vol = (long long)S * S * S;
+        const int c_base = p.nt_off[nt];
+        for (int a = 0; a < AD; ++a) {
+            const int d = d0 + a;
+            const bool ok = (d < S) && (h < S) && (w < S);             // warp-uniform loads, predicated stores
+            const long long vox = ((long long)d * S + h) * S + w;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N);
+            float z = 0.f;
+            for (int j = 0; j < N; j += 16) {
+                uint32_t v[16];
+                tc_ld16(trow + j, v);
+                tc_ld_wait();
+                float y[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = c_base + j + i;
+                    y[i] = tc_act(fmaf(__uint_as_float(v[i]), __ldg(p.scale + c), __ldg(p.shift + c)), p.act);
+                }
+                if (p.epi == EPI_FINAL) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (j + i < p.c3) z = fmaf(y[i], __ldg(p.w3 + j + i), z);
+                } else if (ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        __half hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            hi[i] = __float2half_rn(y[8 * g + i]);
+                            lo[i] = __float2half_rn(y[8 * g + i] - __half2float(hi[i]));
+                        }
+                        const int cg = p.cg_out_off + ((c_base + j) >> 3) + g;
+                        __half* dst = p.out + (((long long)pc * P) * p.cg_out_total + cg) * vol * 8 + vox * 8;
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+                        if (P == 2)
+                            *reinterpret_cast<uint4*>(dst + (long long)p.cg_out_total * vol * 8) =
+                                make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+                    }
+                }
+            }
+            if (p.epi == EPI_FINAL && ok)
+                p.prob_out[(long long)pc * vol + vox] = 1.f / (1.f + expf(-fmaf(z, p.scale3, p.shift3)));
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small blk-format kernels (HBM-bound)
+
+// fp32 NCDHW (n, C, vol) -> blk (n, P, cg, vol, 8); channels >= C are zero
+__global__ void pack_blk_kernel(const float* __restrict__ x, int C, int cg, int P, long long vol, long long total, __half* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {                     // i over (n, g, voxel)
+        const long long vox = i % vol;
+        const int g = (int)((i / vol) % cg);
+        const long long n = i / (vol * cg);
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            const float v = (c < C) ? __ldg(x + (n * C + c) * vol + vox) : 0.f;
+            hi[k] = __float2half_rn(v);
+            lo[k] = __float2half_rn(v - __half2float(hi[k]));
+        }
+        __half* dst = out + ((n * P) * cg + g) * vol * 8 + vox * 8;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+        if (P == 2)
+            *reinterpret_cast<uint4*>(dst + (long long)cg * vol * 8) =
+                make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+    }
+}
+
+__device__ __forceinline__ void load_blk8(const __half* src, long long prec_stride, int P, float (&v)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(ha[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+    if (P == 2) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + prec_stride));
+        const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hb[k]); v[2 * k] += f.x; v[2 * k + 1] += f.y; }
+    }
+}
+
+__device__ __forceinline__ void store_blk8(__half* dst, long long prec_stride, int P, const float (&v)[8]) {
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { hi[k] = __float2half_rn(v[k]); lo[k] = __float2half_rn(v[k] - __half2float(hi[k])); }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+    if (P == 2)
+        *reinterpret_cast<uint4*>(dst + prec_stride) = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+}
+
+// blk -> fp32 NCDHW (first C channels)
+__global__ void unpack_blk_kernel(const __half* __restrict__ in, int C, int cg, int P, long long vol, long long total, float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long vox = i % vol;
+        const int g = (int)((i / vol) % cg);
+        const long long n = i / (vol * cg);
+        float v[8];
+        load_blk8(in + ((n * P) * cg + g) * vol * 8 + vox * 8, (long long)cg * vol * 8, P, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (g * 8 + k < C) out[(n * C + g * 8 + k) * vol + vox] = v[k];
+    }
+}
+
+// 2^3 / stride-2 max pool, blk -> blk                                        nets/SurfaceNet.py:37,46
+__global__ void pool_blk_kernel(const __half* __restrict__ in, int cg, int P, int S, long long total, __half* __restrict__ out) {
+    const int So = S / 2;
+    const long long vol = (long long)S * S * S, volo = (long long)So * So * So;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {                     // (n, g, od, oh, ow)
+        const int ow = (int)(i % So), oh = (int)((i / So) % So), od = (int)((i / ((long long)So * So)) % So);
+        const int g = (int)((i / volo) % cg);
+        const long long n = i / (volo * cg);
+        const __half* base = in + ((n * P) * cg + g) * vol * 8;
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float v[8];
+                    load_blk8(base + (((long long)(2 * od + a) * S + 2 * oh + b) * S + 2 * ow + c) * 8, (long long)cg * vol * 8, P, v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+                }
+        store_blk8(out + ((n * P) * cg + g) * volo * 8 + (((long long)od * So + oh) * So + ow) * 8, (long long)cg * volo * 8, P, m);
+    }
+}
+
+// zero-stuff by f + fixed k^3 conv ('same'), blk (cg_in groups at S) -> groups [cg_off, cg_off + cg_in) of a blk
+// tensor with cg_total groups at f*S                                          nets/layers.py:376-390, SurfaceNet.py:71
+__global__ void upsample_blk_kernel(const __half* __restrict__ in, const float* __restrict__ W, int k, int f, int cg_in, int P, int S,
+                                    long long total, __half* __restrict__ out, int cg_total, int cg_off) {
+    const int So = S * f, c0 = k / 2;
+    const long long vol = (long long)S * S * S, volo = (long long)So * So * So;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int ow = (int)(i % So), oh = (int)((i / So) % So), od = (int)((i / ((long long)So * So)) % So);
+        const int g = (int)((i / volo) % cg_in);
+        const long long n = i / (volo * cg_in);
+        const __half* base = in + ((n * P) * cg_in + g) * vol * 8;
+        const int td0 = ((c0 - od) % f + f) % f, th0 = ((c0 - oh) % f + f) % f, tw0 = ((c0 - ow) % f + f) % f;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int td = td0; td < k; td += f) {
+            const int pd = od + td - c0;
+            if (pd < 0 || pd >= So) continue;
+            for (int th = th0; th < k; th += f) {
+                const int ph = oh + th - c0;
+                if (ph < 0 || ph >= So) continue;
+                for (int tw = tw0; tw < k; tw += f) {
+                    const int pw = ow + tw - c0;
+                    if (pw < 0 || pw >= So) continue;
+                    const float wt = __ldg(W + (td * k + th) * k + tw);
+                    float v[8];
+                    load_blk8(base + (((long long)(pd / f) * S + ph / f) * S + pw / f) * 8, (long long)cg_in * vol * 8, P, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] = fmaf(wt, v[q], acc[q]);
+                }
+            }
+        }
+        store_blk8(out + ((n * P) * cg_total + cg_off + g) * volo * 8 + (((long long)od * So + oh) * So + ow) * 8,
+                   (long long)cg_total * volo * 8, P, acc);
+    }
+}
+
+static inline int ew_blocks(long long total) { return (int)std::min<long long>(cdiv(total, 256), 148 * 16); }
+
+// ------------------------------------------------------------------------------------------------
+// host side: weight preparation, tensor maps, launches
+struct TcUnit {
+    int n_ntiles = 0, nt_size[2] = {0, 0}, nt_off[2] = {0, 0};
+    int Cin_pad = 0, Cout_pad = 0, taps = 0;
+    unsigned char* w[2] = {nullptr, nullptr};      // [0] exact (P = 2), [1] fast (P = 1)
+    long long nt_woff[2][2] = {{0, 0}, {0, 0}};    // [variant][ntile]
+    float* scale = nullptr;                        // Cout_pad (+ slack to a multiple of 16 per N tile)
+    float* shift = nullptr;
+};
+
+struct TcState {
+    TcUnit units[kNumUnits];
+    float* w3 = nullptr; float scale3 = 0.f, shift3 = 0.f;
+    PFN_cuTensorMapEncodeTiled encode = nullptr;
+};
+
+static int pad16(int c) { return (int)align_up(c, 16); }
+
+int tc_prepare(Net& net) {
+    TcState* st = new TcState();
+    net.tc = st;
+    for (int u = 0; u < kNumUnits; ++u) {
+        const ConvUnit& cu = net.units[u];
+        if (cu.kind == UNIT_UP) continue;
+        TcUnit& tu = st->units[u];
+        const int K3 = cu.K * cu.K * cu.K;
+        tu.taps = K3;
+        tu.Cin_pad = pad16(cu.Cin);
+        tu.Cout_pad = pad16(cu.Cout);
+        if (tu.Cout_pad <= 256) { tu.n_ntiles = 1; tu.nt_size[0] = tu.Cout_pad; tu.nt_off[0] = 0; }
+        else { tu.n_ntiles = 2; tu.nt_size[0] = pad16(tu.Cout_pad / 2); tu.nt_off[0] = 0; tu.nt_size[1] = tu.Cout_pad - tu.nt_size[0]; tu.nt_off[1] = tu.nt_size[0]; }
+        // power-of-two pre-scaling so that hi and lo are both normal fp16 numbers; undone in the folded BatchNorm scale
+        float wmax = 0.f;
+        for (float v : cu.h_w) wmax = std::max(wmax, fabsf(v));
+        int e = 0;
+        if (wmax > 0.f) { e = (int)floorf(log2f(1024.f / wmax)); e = std::max(-14, std::min(24, e)); }
+        const float wscale = ldexpf(1.f, e), inv = ldexpf(1.f, -e);
+        const int n_cblk = tu.Cin_pad / 16;
+        for (int variant = 0; variant < 2; ++variant) {
+            const int P = variant == 0 ? 2 : 1;
+            size_t bytes = 0;
+            for (int t = 0; t < tu.n_ntiles; ++t) { tu.nt_woff[variant][t] = (long long)bytes; bytes += (size_t)n_cblk * K3 * P * tu.nt_size[t] * 32; }
+            std::vector<__half> h(bytes / 2, __float2half_rn(0.f));
+            for (int t = 0; t < tu.n_ntiles; ++t) {
+                const int N = tu.nt_size[t];
+                __half* base = h.data() + tu.nt_woff[variant][t] / 2;
+                for (int cb = 0; cb < n_cblk; ++cb)
+                    for (int tap = 0; tap < K3; ++tap)
+                        for (int nn = 0; nn < N; ++nn)
+                            for (int kk = 0; kk < 16; ++kk) {
+                                const int co = tu.nt_off[t] + nn, ci = cb * 16 + kk;
+                                if (co >= cu.Cout || ci >= cu.Cin) continue;
+                                const float wv = cu.h_w[((size_t)co * cu.Cin + ci) * K3 + tap] * wscale;
+                                const __half hi = __float2half_rn(wv);
+                                const __half lo = __float2half_rn(wv - __half2float(hi));
+                                // stage = [prec][kg = kk/8][ng = nn/8][nn%8][kk%8]
+                                const size_t stage = ((size_t)cb * K3 + tap) * P * N * 16;
+                                const size_t idx = (size_t)(kk / 8) * N * 8 + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (kk % 8);
+                                base[stage + idx] = hi;
+                                if (P == 2) base[stage + (size_t)N * 16 + idx] = lo;
+                            }
+            }
+            SN_CUDA(cudaMalloc((void**)&tu.w[variant], bytes));
+            SN_CUDA(cudaMemcpy(tu.w[variant], h.data(), bytes, cudaMemcpyHostToDevice));
+        }
+        std::vector<float> sc(tu.Cout_pad, 0.f), sh(tu.Cout_pad, 0.f);
+        for (int c = 0; c < cu.Cout; ++c) { sc[c] = cu.h_scale[c] * inv; sh[c] = cu.h_shift[c]; }
+        SN_CUDA(cudaMalloc((void**)&tu.scale, sc.size() * 4));
+        SN_CUDA(cudaMalloc((void**)&tu.shift, sh.size() * 4));
+        SN_CUDA(cudaMemcpy(tu.scale, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
+        SN_CUDA(cudaMemcpy(tu.shift, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice));
+    }
+    {   // merge_conv3 for the fused epilogue of merge_conv2
+        const ConvUnit& m3 = net.units[U_MERGE3];
+        std::vector<float> w3(pad16(m3.Cin), 0.f);
+        for (int c = 0; c < m3.Cin; ++c) w3[c] = m3.h_w[c];
+        SN_CUDA(cudaMalloc((void**)&st->w3, w3.size() * 4));
+        SN_CUDA(cudaMemcpy(st->w3, w3.data(), w3.size() * 4, cudaMemcpyHostToDevice));
+        st->scale3 = m3.h_scale[0]; st->shift3 = m3.h_shift[0];
+    }
+    return SN_OK;
+}
+
+void tc_destroy(Net& net) {
+    TcState* st = (TcState*)net.tc;
+    if (!st) return;
+    for (int u = 0; u < kNumUnits; ++u) {
+        cudaFree(st->units[u].w[0]); cudaFree(st->units[u].w[1]); cudaFree(st->units[u].scale); cudaFree(st->units[u].shift);
+    }
+    cudaFree(st->w3);
+    delete st;
+    net.tc = nullptr;
+}
+
+static int get_encode(TcState* st) {
+    if (st->encode) return SN_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return SN_ERR_CUDA; }
+    st->encode = (PFN_cuTensorMapEncodeTiled)fn;
+    return SN_OK;
+}
+
+struct TileCfg { int AD, NB; };
+
+// accumulators per CTA (planes) and weight-ring depth per unit; bounded by 512 TMEM columns and 227 KB smem
+static TileCfg tile_cfg(const ConvUnit& cu, const TcUnit& tu, int S, int P) {
+    const int Nmax = std::max(tu.nt_size[0], tu.nt_size[1]);
+    int AD = std::min(4, 512 / Nmax);
+    if (cu.dil == 2 && cu.K == 3) AD = std::min(AD, 2);
+    AD = std::max(1, std::min(AD, S));
+    const int pad = cu.dil * (cu.K / 2);
+    const int PW = TC_TW + 2 * pad, HH = TC_TH + 2 * pad;
+    int NB = 4;
+    while (NB > 2 && 2ll * PW * HH * (AD + 2 * pad) * 32 * P + (long long)NB * Nmax * 32 * P + 1024 > 227 * 1024) --NB;
+    return {AD, NB};
+}
+
+// in: blk (n_pc, P, Cin_pad/8, S^3, 8).  EPI_BLK: out blk with cg_out_total groups, written at cg_out_off.
+static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int S, int P, int epi, __half* out, int cg_out_total,
+                          int cg_out_off, float* prob_out, cudaStream_t stream) {
+    TcState* st = (TcState*)net.tc;
+    const ConvUnit& cu = net.units[u];
+    const TcUnit& tu = st->units[u];
+    int rc = get_encode(st);
+    if (rc != SN_OK) return rc;
+    const TileCfg cfg = tile_cfg(cu, tu, S, P);
+    ConvTcParams p{};
+    p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.n_cblk = tu.Cin_pad / 16; p.cg_in = tu.Cin_pad / 8;
+    p.P = P; p.AD = cfg.AD; p.NB = cfg.NB;
+    const int pad = cu.dil * (cu.K / 2);
+    p.PW = TC_TW + 2 * pad; p.HH = TC_TH + 2 * pad; p.HD = p.AD + 2 * pad;
+    p.a_prec_bytes = p.PW * p.HH * p.HD * 32;
+    p.tiles_w = (int)cdiv(S, TC_TW); p.tiles_h = (int)cdiv(S, TC_TH); p.tiles_d = (int)cdiv(S, p.AD);
+    p.n_ntiles = tu.n_ntiles;
+    const int variant = (P == 2) ? 0 : 1;
+    for (int t = 0; t < 2; ++t) { p.nt_size[t] = tu.nt_size[t]; p.nt_off[t] = tu.nt_off[t]; p.nt_woff[t] = tu.nt_woff[variant][t]; }
+    p.weights = tu.w[variant]; p.scale = tu.scale; p.shift = tu.shift; p.act = cu.act; p.epi = epi;
+    p.out = out; p.cg_out_total = cg_out_total; p.cg_out_off = cg_out_off;
+    p.w3 = st->w3; p.scale3 = st->scale3; p.shift3 = st->shift3; p.c3 = net.units[U_MERGE3].Cin; p.prob_out = prob_out;
+
+    CUtensorMap map;
+    const cuuint64_t gdim[4] = {(cuuint64_t)8 * S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)n_pc * P * p.cg_in};
+    const cuuint64_t gstr[3] = {(cuuint64_t)S * 16, (cuuint64_t)S * S * 16, (cuuint64_t)S * S * S * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)(8 * p.PW), (cuuint32_t)p.HH, (cuuint32_t)p.HD, 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = st->encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for unit %s, S=%d", (int)cr, kUnits[u].name, S); return SN_ERR_CUDA; }
+
+    const int Nmax = std::max(tu.nt_size[0], tu.nt_size[1]);
+    const size_t smem = 2 * (size_t)p.a_prec_bytes * P + (size_t)p.NB * Nmax * 32 * P + (5 + 2 * p.NB) * 8 + 16;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        SN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_smem = 227 * 1024;
+    }
+    const long long tiles = (long long)n_pc * p.tiles_d * p.tiles_h * p.tiles_w;
+    SN_CHECK_ARG(tiles <= 0x7fffffff && smem <= 227 * 1024, "conv_tc: launch too large (tiles=%lld smem=%zu)", tiles, smem);
+    dim3 grid((unsigned)tiles, (unsigned)tu.n_ntiles);
+    prof_begin(u, stream);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(map, p);
+    prof_end(u, stream);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+
+static int pack_launch(const float* x, int n, int C, int Cpad, int P, long long vol, __half* out, cudaStream_t st) {
+    const long long total = (long long)n * (Cpad / 8) * vol;
+    if (!total) return SN_OK;
+    pack_blk_kernel<<<ew_blocks(total), 256, 0, st>>>(x, C, Cpad / 8, P, vol, total, out);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+static int unpack_launch(const __half* in, int n, int C, int Cpad, int P, long long vol, float* out, cudaStream_t st) {
+    const long long total = (long long)n * (Cpad / 8) * vol;
+    if (!total) return SN_OK;
+    unpack_blk_kernel<<<ew_blocks(total), 256, 0, st>>>(in, C, Cpad / 8, P, vol, total, out);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+static int pool_launch(const __half* in, int n, int Cpad, int P, int S, __half* out, cudaStream_t st) {
+    const long long total = (long long)n * (Cpad / 8) * (S / 2) * (S / 2) * (S / 2);
+    if (!total) return SN_OK;
+    pool_blk_kernel<<<ew_blocks(total), 256, 0, st>>>(in, Cpad / 8, P, S, total, out);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+static int upsample_blk_launch(const __half* in, const float* W, int k, int f, int n, int Cpad, int P, int S, __half* out, int cg_total,
+                               int cg_off, cudaStream_t st) {
+    const long long total = (long long)n * (Cpad / 8) * S * f * S * f * S * f;
+    if (!total) return SN_OK;
+    upsample_blk_kernel<<<ew_blocks(total), 256, 0, st>>>(in, W, k, f, Cpad / 8, P, S, total, out, cg_total, cg_off);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+
+// halfs of workspace per pair-cube (per precision plane)
+static long long tc_halfs_per_pc(int D) {
+    const long long V = (long long)D * D * D, V2 = V / 8, V4 = V / 64;
+    return V * (16 + 32 + 32 + 64 + 112) + V2 * (32 + 80 + 80 + 16) + V4 * (80 + 160 + 160 + 16 + 304 + 304 + 16);
+}
+constexpr int kTcMaxChunk = 64;
+
+int64_t tc_workspace_bytes(const Net& net, int n_pc, int D, int mode) {
+    (void)net;
+    const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
+    return align_up(tc_halfs_per_pc(D) * 2 * P * std::min(n_pc, kTcMaxChunk), 256) + 4096;
+}
+
+static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float* prob_out, __half* ws, int P, cudaStream_t st) {
+    const long long V = (long long)D * D * D, V2 = V / 8, V4 = V / 64;
+    const int S1 = D, S2 = D / 2, S4 = D / 4;
+    const long long np = (long long)n * P;
+    __half* x0 = ws;               __half* a1 = x0 + 16 * V * np;  __half* a2 = a1 + 32 * V * np;  __half* cat = a2 + 32 * V * np;
+    __half* m1 = cat + 64 * V * np; __half* p1 = m1 + 112 * V * np; __half* b1 = p1 + 32 * V2 * np; __half* b2 = b1 + 80 * V2 * np;
+    __half* s2 = b2 + 80 * V2 * np; __half* p2 = s2 + 16 * V2 * np; __half* c1 = p2 + 80 * V4 * np; __half* c2 = c1 + 160 * V4 * np;
+    __half* s3 = c2 + 160 * V4 * np; __half* d1 = s3 + 16 * V4 * np; __half* d2 = d1 + 304 * V4 * np; __half* s4 = d2 + 304 * V4 * np;
+    const ConvUnit* U = net.units;
+    int rc;
+#define RUN(x) do { rc = (x); if (rc != SN_OK) return rc; } while (0)
+#define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))
+    RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
+    CONV(U_CONV1_1, x0, S1, a1, 4, 0);
+    CONV(U_CONV1_2, a1, S1, a2, 4, 0);
+    CONV(U_CONV1_3, a2, S1, a1, 4, 0);
+    CONV(U_SIDE1, a1, S1, cat, 8, 0);                                             // side_op1 -> concat[0:16]
+    RUN(pool_launch(a1, n, 32, P, S1, p1, st));
+    CONV(U_CONV2_1, p1, S2, b1, 10, 0);
+    CONV(U_CONV2_2, b1, S2, b2, 10, 0);
+    CONV(U_CONV2_3, b2, S2, b1, 10, 0);
+    CONV(U_SIDE2, b1, S2, s2, 2, 0);
+    RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, st));   // -> concat[16:32]
+    RUN(pool_launch(b1, n, 80, P, S2, p2, st));
+    CONV(U_CONV3_1, p2, S4, c1, 20, 0);
+    CONV(U_CONV3_2, c1, S4, c2, 20, 0);
+    CONV(U_CONV3_3, c2, S4, c1, 20, 0);
+    CONV(U_SIDE3, c1, S4, s3, 2, 0);
+    RUN(upsample_blk_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, P, S4, cat, 8, 4, st));   // -> concat[32:48]
+    CONV(U_CONV4_1, c1, S4, d1, 38, 0);
+    CONV(U_CONV4_2, d1, S4, d2, 38, 0);
+    CONV(U_CONV4_3, d2, S4, d1, 38, 0);
+    CONV(U_SIDE4, d1, S4, s4, 2, 0);
+    RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, st));   // -> concat[48:64]
+    CONV(U_MERGE1, cat, S1, m1, 14, 0);
+    RUN(conv_tc_launch(net, U_MERGE2, m1, n, S1, P, EPI_FINAL, nullptr, 0, 0, prob_out, st));   // + merge_conv3 + sigmoid
+#undef CONV
+#undef RUN
+    return SN_OK;
+}
+
 int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out, void* ws, int64_t ws_bytes, int mode, cudaStream_t st) {
-    (void)net; (void)X; (void)n_pc; (void)D; (void)prob_out; (void)ws; (void)ws_bytes; (void)mode; (void)st;
-    set_error("tensor-core modes are not available in this build");
-    return SN_ERR_INVALID;
+    const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
+    const int64_t need = tc_workspace_bytes(net, n_pc, D, mode);
+    if (!ws || ws_bytes < need) { set_error("tensor-core forward: workspace %lld B < %lld B", (long long)ws_bytes, (long long)need); return SN_ERR_NOMEM; }
+    const long long V = (long long)D * D * D;
+    const int chunk = std::min(n_pc, kTcMaxChunk);
+    __half* w = (__half*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    for (int i = 0; i < n_pc; i += chunk) {
+        const int n = std::min(chunk, n_pc - i);
+        int rc = tc_forward_chunk(net, X + (long long)i * 6 * V, n, D, prob_out + (long long)i * V, w, P, st);
+        if (rc != SN_OK) return rc;
+    }
+    return SN_OK;
+}
+
+// single conv unit through the tensor-core path, fp32 NCDHW in / out (tests, calibration)
+int tc_layer_conv(const Net& net, int u, const float* in, int n, int S, float* out, int mode, cudaStream_t st) {
+    const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
+    TcState* ts = (TcState*)net.tc;
+    const ConvUnit& cu = net.units[u];
+    const TcUnit& tu = ts->units[u];
+    const long long vol = (long long)S * S * S;
+    __half *bi = nullptr, *bo = nullptr;
+    SN_CUDA(cudaMallocAsync((void**)&bi, (size_t)n * P * tu.Cin_pad * vol * 2 + 1024, st));
+    SN_CUDA(cudaMallocAsync((void**)&bo, (size_t)n * P * tu.Cout_pad * vol * 2 + 1024, st));
+    int rc = pack_launch(in, n, cu.Cin, tu.Cin_pad, P, vol, bi, st);
+    if (rc == SN_OK) rc = conv_tc_launch(net, u, bi, n, S, P, EPI_BLK, bo, tu.Cout_pad / 8, 0, nullptr, st);
+    if (rc == SN_OK) rc = unpack_launch(bo, n, cu.Cout, tu.Cout_pad, P, vol, out, st);
+    cudaFreeAsync(bi, st); cudaFreeAsync(bo, st);
+    return rc;
 }
 
 }  // namespace sn

@@ -175,11 +175,15 @@ extern "C" void sn_net_destroy(sn_net* h) {
 }
 
 // ---- single layers -------------------------------------------------------------------------------
-extern "C" int sn_net_layer_conv(const sn_net* h, int unit, const float* in_dev, int n, int S, float* out_dev, void* stream) {
+namespace sn { int tc_layer_conv(const Net& net, int u, const float* in, int n, int S, float* out, int mode, cudaStream_t st); }
+
+extern "C" int sn_net_layer_conv(const sn_net* h, int unit, const float* in_dev, int n, int S, float* out_dev, int mode, void* stream) {
     SN_CHECK_ARG(h && in_dev && out_dev, "sn_net_layer_conv: NULL argument");
     SN_CHECK_ARG(unit >= 0 && unit < kNumUnits && kUnits[unit].kind != UNIT_UP, "sn_net_layer_conv: unit %d is not a conv unit", unit);
     SN_CHECK_ARG(n >= 0 && S >= 1, "sn_net_layer_conv: bad sizes");
+    SN_CHECK_ARG(mode == SN_MODE_FP32 || mode == SN_MODE_TC_EXACT || mode == SN_MODE_TC_FAST, "sn_net_layer_conv: unknown mode %d", mode);
     if (n == 0) return SN_OK;
+    if (mode != SN_MODE_FP32) return tc_layer_conv(h->net, unit, in_dev, n, S, out_dev, mode, (cudaStream_t)stream);
     return conv_fp32_launch(h->net.units[unit], in_dev, n, S, out_dev, kUnits[unit].Cout, 0, (cudaStream_t)stream);
 }
 

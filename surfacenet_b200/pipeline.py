@@ -89,6 +89,10 @@ class HotPath:
         B, n_vp = self._check_batch(pairs, np.asarray(xyz), np.asarray(resol), None if w is None else np.asarray(w))
         self.scene.check_views(pairs)
         D = int(D)
+        if B == 0:                                  # main_reconstruct.py:128-129: an empty selection is not an error
+            self.h2d_bytes = self.d2h_bytes = 0
+            return dict(fused=np.zeros((0, 1, D, D, D), np.float32) if want_fused else None, pred16=np.zeros((0, D, D, D), np.float16),
+                        votes=np.zeros((0, D, D, D), np.uint8) if ray_pool else None)
         h_pairs = self._pin("pairs", (B, n_vp, 2), t.int32); h_pairs.numpy()[...] = pairs
         h_xyz = self._pin("xyz", (B, 3), t.float32); h_xyz.numpy()[...] = xyz
         h_resol = self._pin("resol", (B,), t.float32); h_resol.numpy()[...] = resol

@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace sn {
 
@@ -45,6 +46,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
+}
+// long waits (epilogue warps waiting for the whole main loop): back off so the spinning warps do not steal issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -88,14 +103,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 constexpr int TC_THREADS = 256;
 constexpr int TC_TW = 8, TC_TH = 16;          // one accumulator = 16 rows (h) x 8 voxels (w) of one d-plane
 constexpr int EPI_BLK = 0, EPI_FINAL = 1;
+constexpr int TC_MAX_NT = 4;
 
 struct ConvTcParams {
-    int S, n_pc, dil, K, taps, n_cblk, cg_in, P, AD, NB;
+    int S, n_pc, dil, K, taps, n_cblk, cg_in, NB;
     int PW, HH, HD;                 // halo tile extents (voxels)
     int a_prec_bytes;               // bytes of one precision plane of one A stage = PW*HH*HD*32
     int tiles_w, tiles_h, tiles_d;
-    int n_ntiles, nt_size[2], nt_off[2];
-    long long nt_woff[2];           // byte offset of the N-tile's weights
+    int n_ntiles, nt_size[TC_MAX_NT], nt_off[TC_MAX_NT];
+    long long nt_woff[TC_MAX_NT];   // byte offset of the N-tile's weights
     const unsigned char* weights;   // [ntile][cblk][tap][prec][kg 2][N/8][8 n][8 k] fp16
     const float* scale;             // folded BatchNorm (x 2^-k of the weight pre-scaling), zero for padded channels
     const float* shift;
@@ -116,11 +132,30 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
+// exactly one lane of the (converged) warp gets true; ptxas then knows the guarded tcgen05 / TMA
+// instruction is issued once and emits it directly instead of a per-lane election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t"
+        "}" : "=r"(pred) :: "memory");
+    return pred != 0;
+}
+
+// AD = d-planes (M = 128 accumulators) per CTA; P = 2: exact mode, every plane owns TWO accumulators -- the
+// main one receives only A_hi*W_hi, the correction one A_lo*W_hi + A_hi*W_lo (2^-11 smaller).  tcgen05
+// truncates (round-toward-zero) once per accumulating MMA, a bias that grows linearly with the number of
+// MMAs into an accumulator; keeping the small terms out of the big accumulator divides that bias by three.
+template <int AD, int P>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int P = p.P, AD = p.AD, NB = p.NB;
+    const int NB = p.NB;
     const int nt = blockIdx.y;
     const int N = p.nt_size[nt];
     const uint32_t a_stage_bytes = (uint32_t)p.a_prec_bytes * P;
@@ -142,7 +177,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
     const int pad = p.dil * (p.K / 2);
 
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < AD * N) tmem_cols <<= 1;
+    while ((int)tmem_cols < AD * P * N) tmem_cols <<= 1;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -162,70 +197,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
 
     if (warp == 0) {
         // ===== A producer: one zero-padded halo tile of 16 channels (x P precisions) per channel block =====
-        if (lane == 0) {
-            for (int cb = 0; cb < p.n_cblk; ++cb) {
-                const int s = cb & 1;
-                mbar_wait(&a_empty[s], ((cb >> 1) & 1) ^ 1);
+        for (int cb = 0; cb < p.n_cblk; ++cb) {
+            const int s = cb & 1;
+            mbar_wait(&a_empty[s], ((cb >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&a_full[s], a_stage_bytes);
+#pragma unroll
                 for (int pr = 0; pr < P; ++pr)
                     tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
                                 8 * (w0 - pad), h0 - pad, d0 - pad, (pc * P + pr) * p.cg_in + 2 * cb);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
         // ===== B producer: the (channel block, tap) weight tile, already in canonical layout in HBM =====
-        if (lane == 0) {
-            const unsigned char* wsrc = p.weights + p.nt_woff[nt];
-            const int total = p.n_cblk * p.taps;
-            for (int it = 0; it < total; ++it) {
-                const int s = it % NB;
-                mbar_wait(&b_empty[s], ((it / NB) & 1) ^ 1);
+        const unsigned char* wsrc = p.weights + p.nt_woff[nt];
+        const int total = p.n_cblk * p.taps;
+        int s = 0; uint32_t ph = 0;
+        for (int it = 0; it < total; ++it) {
+            mbar_wait(&b_empty[s], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&b_full[s], b_stage_bytes);
                 bulk_load(smB + (size_t)s * b_stage_bytes, wsrc + (size_t)it * b_stage_bytes, b_stage_bytes, &b_full[s]);
             }
+            __syncwarp();
+            if (++s == NB) { s = 0; ph ^= 1; }
         }
     } else if (warp == 2) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, N, M=128
-            const uint32_t lbo_a = (uint32_t)p.a_prec_bytes / 2, sbo_a = (uint32_t)p.PW * 16;
-            const uint32_t lbo_b = (uint32_t)N * 16, sbo_b = 128;
-            const uint32_t smA_u = smem_u32(smA), smB_u = smem_u32(smB);
-            int it = 0;
-            for (int cb = 0; cb < p.n_cblk; ++cb) {
-                const int sa = cb & 1;
-                mbar_wait(&a_full[sa], (cb >> 1) & 1);
-                tc_fence_after();
-                const uint32_t a_hi = smA_u + sa * a_stage_bytes, a_lo = a_hi + p.a_prec_bytes;
-                for (int tap = 0; tap < p.taps; ++tap, ++it) {
-                    const int sb = it % NB;
-                    mbar_wait(&b_full[sb], (it / NB) & 1);
-                    tc_fence_after();
-                    const int kw = tap % p.K, kh = (tap / p.K) % p.K, kd = tap / (p.K * p.K);
-                    const uint32_t b_hi = smB_u + sb * b_stage_bytes;
-                    const uint64_t db_hi = make_desc(b_hi, lbo_b, sbo_b);
-                    const uint64_t db_lo = make_desc(b_hi + b_prec_bytes, lbo_b, sbo_b);
-                    const uint32_t first = (it == 0) ? 0u : 1u;
-                    for (int a = 0; a < AD; ++a) {
-                        const uint32_t off = (uint32_t)((((a + kd * p.dil) * p.HH + kh * p.dil) * p.PW + kw * p.dil) * 16);
-                        const uint32_t dcol = tmem_base + (uint32_t)(a * N);
-                        const uint64_t da_hi = make_desc(a_hi + off, lbo_a, sbo_a);
-                        tc_mma(dcol, da_hi, db_hi, idesc, first);
-                        if (P == 2) {
-                            const uint64_t da_lo = make_desc(a_lo + off, lbo_a, sbo_a);
-                            tc_mma(dcol, da_lo, db_hi, idesc, 1u);
-                            tc_mma(dcol, da_hi, db_lo, idesc, 1u);
+        // ===== MMA issuer: the warp stays converged, one elected lane issues =====
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, N, M=128
+        // descriptor words (units of 16 B): hi = SBO | version 1, lo = start | LBO << 16
+        const uint32_t a_hi32 = (uint32_t)p.PW | (1u << 14);
+        const uint32_t b_hi32 = 8u | (1u << 14);
+        const uint32_t a_lbo = (uint32_t)(p.a_prec_bytes >> 5) << 16;        // one channel-group plane of the halo tile
+        const uint32_t b_lbo = (uint32_t)N << 16;                            // N * 16 B
+        const uint32_t smA16 = smem_u32(smA) >> 4, smB16 = smem_u32(smB) >> 4;
+        const uint32_t a_stage16 = a_stage_bytes >> 4, a_prec16 = (uint32_t)p.a_prec_bytes >> 4;
+        const uint32_t b_stage16 = b_stage_bytes >> 4, b_prec16 = b_prec_bytes >> 4;
+        const uint32_t plane16 = (uint32_t)(p.HH * p.PW), row16 = (uint32_t)p.PW;
+        const uint32_t dil = (uint32_t)p.dil;
+        int sb = 0; uint32_t phb = 0, acc_flag = 0;
+        for (int cb = 0; cb < p.n_cblk; ++cb) {
+            const int sa = cb & 1;
+            mbar_wait(&a_full[sa], (cb >> 1) & 1);
+            tc_fence_after();
+            const uint32_t a_lo32 = (smA16 + sa * a_stage16) | a_lbo;
+            for (int kd = 0; kd < p.K; ++kd)
+                for (int kh = 0; kh < p.K; ++kh)
+                    for (int kw = 0; kw < p.K; ++kw) {
+                        const uint32_t tap16 = (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
+                        mbar_wait(&b_full[sb], phb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t db_hi = ((uint64_t)b_hi32 << 32) | ((smB16 + sb * b_stage16) | b_lbo);
+                            const uint64_t db_lo = db_hi + b_prec16;
+#pragma unroll
+                            for (int a = 0; a < AD; ++a) {
+                                const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (a_lo32 + tap16 + a * plane16);
+                                tc_mma(tmem_base + (uint32_t)(a * N), da_hi, db_hi, idesc, acc_flag);
+                                if (P == 2) {
+                                    const uint64_t da_lo = da_hi + a_prec16;
+                                    const uint32_t dcorr = tmem_base + (uint32_t)((AD + a) * N);
+                                    tc_mma(dcorr, da_lo, db_hi, idesc, acc_flag);
+                                    tc_mma(dcorr, da_hi, db_lo, idesc, 1u);
+                                }
+                            }
+                            tc_commit(&b_empty[sb]);              // weight stage free once these MMAs retire
                         }
+                        __syncwarp();
+                        acc_flag = 1u;
+                        if (++sb == NB) { sb = 0; phb ^= 1; }
                     }
-                    tc_commit(&b_empty[sb]);              // weight stage free once these MMAs retire
-                }
-                tc_commit(&a_empty[sa]);
-            }
-            tc_commit(acc_full);
+            if (elect_one()) tc_commit(&a_empty[sa]);
+            __syncwarp();
         }
+        if (elect_one()) tc_commit(acc_full);
+        __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue: TMEM lane quarter (warp % 4) -> rows m = 32 q + lane -> voxel (h0 + m/8, w0 + m%8) =====
-        mbar_wait(acc_full, 0);
+        mbar_wait_sleep(acc_full, 0);
         tc_fence_after();
         const int q = warp & 3;
         const int m = q * 32 + lane;
@@ -233,16 +283,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
         const int S = p.S;
         const long long vol = (long long)S * S * S;
         const int c_base = p.nt_off[nt];
+#pragma unroll 1
         for (int a = 0; a < AD; ++a) {
             const int d = d0 + a;
             const bool ok = (d < S) && (h < S) && (w < S);             // warp-uniform loads, predicated stores
             const long long vox = ((long long)d * S + h) * S + w;
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * N);
             float z = 0.f;
+#pragma unroll 1
             for (int j = 0; j < N; j += 16) {
                 uint32_t v[16];
                 tc_ld16(trow + j, v);
-                tc_ld_wait();
+                if (P == 2) {
+                    uint32_t c[16];
+                    tc_ld16(trow + (uint32_t)(AD * N) + j, c);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
+                } else {
+                    tc_ld_wait();
+                }
                 float y[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -420,12 +480,15 @@ static inline int ew_blocks(long long total) { return (int)std::min<long long>(c
 
 // ------------------------------------------------------------------------------------------------
 // host side: weight preparation, tensor maps, launches
+struct TcVariant {                                 // [0] exact (P = 2), [1] fast (P = 1): own N tiling and weight image
+    int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0};
+    long long nt_woff[TC_MAX_NT] = {0, 0, 0, 0};
+    unsigned char* w = nullptr;
+};
 struct TcUnit {
-    int n_ntiles = 0, nt_size[2] = {0, 0}, nt_off[2] = {0, 0};
     int Cin_pad = 0, Cout_pad = 0, taps = 0;
-    unsigned char* w[2] = {nullptr, nullptr};      // [0] exact (P = 2), [1] fast (P = 1)
-    long long nt_woff[2][2] = {{0, 0}, {0, 0}};    // [variant][ntile]
-    float* scale = nullptr;                        // Cout_pad (+ slack to a multiple of 16 per N tile)
+    TcVariant v[2];
+    float* scale = nullptr;                        // Cout_pad entries, zero for padded channels
     float* shift = nullptr;
 };
 
@@ -448,8 +511,6 @@ int tc_prepare(Net& net) {
         tu.taps = K3;
         tu.Cin_pad = pad16(cu.Cin);
         tu.Cout_pad = pad16(cu.Cout);
-        if (tu.Cout_pad <= 256) { tu.n_ntiles = 1; tu.nt_size[0] = tu.Cout_pad; tu.nt_off[0] = 0; }
-        else { tu.n_ntiles = 2; tu.nt_size[0] = pad16(tu.Cout_pad / 2); tu.nt_off[0] = 0; tu.nt_size[1] = tu.Cout_pad - tu.nt_size[0]; tu.nt_off[1] = tu.nt_size[0]; }
         // power-of-two pre-scaling so that hi and lo are both normal fp16 numbers; undone in the folded BatchNorm scale
         float wmax = 0.f;
         for (float v : cu.h_w) wmax = std::max(wmax, fabsf(v));
@@ -458,18 +519,27 @@ int tc_prepare(Net& net) {
         const float wscale = ldexpf(1.f, e), inv = ldexpf(1.f, -e);
         const int n_cblk = tu.Cin_pad / 16;
         for (int variant = 0; variant < 2; ++variant) {
+            TcVariant& tv = tu.v[variant];
             const int P = variant == 0 ? 2 : 1;
+            // N tiling: exact mode needs 2 accumulators per plane (<= 512 TMEM columns for >= 2 planes) -> tiles <= 112
+            const int cap = (P == 2) ? 112 : 256;
+            tv.n_ntiles = (int)cdiv(tu.Cout_pad, cap);
+            int left = tu.Cout_pad, off = 0;
+            for (int t = 0; t < tv.n_ntiles; ++t) {
+                const int sz = pad16((int)cdiv(left, tv.n_ntiles - t));
+                tv.nt_size[t] = std::min(sz, left); tv.nt_off[t] = off; off += tv.nt_size[t]; left -= tv.nt_size[t];
+            }
             size_t bytes = 0;
-            for (int t = 0; t < tu.n_ntiles; ++t) { tu.nt_woff[variant][t] = (long long)bytes; bytes += (size_t)n_cblk * K3 * P * tu.nt_size[t] * 32; }
+            for (int t = 0; t < tv.n_ntiles; ++t) { tv.nt_woff[t] = (long long)bytes; bytes += (size_t)n_cblk * K3 * P * tv.nt_size[t] * 32; }
             std::vector<__half> h(bytes / 2, __float2half_rn(0.f));
-            for (int t = 0; t < tu.n_ntiles; ++t) {
-                const int N = tu.nt_size[t];
-                __half* base = h.data() + tu.nt_woff[variant][t] / 2;
+            for (int t = 0; t < tv.n_ntiles; ++t) {
+                const int N = tv.nt_size[t];
+                __half* base = h.data() + tv.nt_woff[t] / 2;
                 for (int cb = 0; cb < n_cblk; ++cb)
                     for (int tap = 0; tap < K3; ++tap)
                         for (int nn = 0; nn < N; ++nn)
                             for (int kk = 0; kk < 16; ++kk) {
-                                const int co = tu.nt_off[t] + nn, ci = cb * 16 + kk;
+                                const int co = tv.nt_off[t] + nn, ci = cb * 16 + kk;
                                 if (co >= cu.Cout || ci >= cu.Cin) continue;
                                 const float wv = cu.h_w[((size_t)co * cu.Cin + ci) * K3 + tap] * wscale;
                                 const __half hi = __float2half_rn(wv);
@@ -481,8 +551,8 @@ int tc_prepare(Net& net) {
                                 if (P == 2) base[stage + (size_t)N * 16 + idx] = lo;
                             }
             }
-            SN_CUDA(cudaMalloc((void**)&tu.w[variant], bytes));
-            SN_CUDA(cudaMemcpy(tu.w[variant], h.data(), bytes, cudaMemcpyHostToDevice));
+            SN_CUDA(cudaMalloc((void**)&tv.w, bytes));
+            SN_CUDA(cudaMemcpy(tv.w, h.data(), bytes, cudaMemcpyHostToDevice));
         }
         std::vector<float> sc(tu.Cout_pad, 0.f), sh(tu.Cout_pad, 0.f);
         for (int c = 0; c < cu.Cout; ++c) { sc[c] = cu.h_scale[c] * inv; sh[c] = cu.h_shift[c]; }
@@ -506,7 +576,7 @@ void tc_destroy(Net& net) {
     TcState* st = (TcState*)net.tc;
     if (!st) return;
     for (int u = 0; u < kNumUnits; ++u) {
-        cudaFree(st->units[u].w[0]); cudaFree(st->units[u].w[1]); cudaFree(st->units[u].scale); cudaFree(st->units[u].shift);
+        cudaFree(st->units[u].v[0].w); cudaFree(st->units[u].v[1].w); cudaFree(st->units[u].scale); cudaFree(st->units[u].shift);
     }
     cudaFree(st->w3);
     delete st;
@@ -525,17 +595,37 @@ static int get_encode(TcState* st) {
 
 struct TileCfg { int AD, NB; };
 
-// accumulators per CTA (planes) and weight-ring depth per unit; bounded by 512 TMEM columns and 227 KB smem
-static TileCfg tile_cfg(const ConvUnit& cu, const TcUnit& tu, int S, int P) {
-    const int Nmax = std::max(tu.nt_size[0], tu.nt_size[1]);
-    int AD = std::min(4, 512 / Nmax);
-    if (cu.dil == 2 && cu.K == 3) AD = std::min(AD, 2);
-    AD = std::max(1, std::min(AD, S));
+// d-planes per CTA and weight-ring depth per unit; bounded by 512 TMEM columns (P accumulators per plane) and 227 KB smem
+static TileCfg tile_cfg(const ConvUnit& cu, const TcVariant& tv, int S, int P) {
+    int Nmax = 0;
+    for (int t = 0; t < tv.n_ntiles; ++t) Nmax = std::max(Nmax, tv.nt_size[t]);
+    int ADmax = std::min(4, 512 / (Nmax * P));
+    if (cu.dil == 2 && cu.K == 3) ADmax = std::min(ADmax, 2);
+    ADmax = std::max(1, std::min(ADmax, S));
+    int AD = ADmax;                                    // largest plane count wasting <= 7 % of the d extent, else the least wasteful
+    double best = -1.0;
+    for (int a = ADmax; a >= 1; --a) {
+        const double eff = (double)S / (double)(cdiv(S, a) * a);
+        if (eff >= 0.93) { AD = a; break; }
+        if (eff > best) { best = eff; AD = a; }
+    }
     const int pad = cu.dil * (cu.K / 2);
     const int PW = TC_TW + 2 * pad, HH = TC_TH + 2 * pad;
-    int NB = 4;
+    static const int env_nb = getenv("SN_TC_NB") ? atoi(getenv("SN_TC_NB")) : 8;
+    int NB = std::max(2, std::min(env_nb, 16));
     while (NB > 2 && 2ll * PW * HH * (AD + 2 * pad) * 32 * P + (long long)NB * Nmax * 32 * P + 1024 > 227 * 1024) --NB;
     return {AD, NB};
+}
+
+template <int AD, int P>
+static int conv_tc_launch_t(const CUtensorMap& map, const ConvTcParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<AD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_tc_kernel<AD, P><<<grid, TC_THREADS, smem, stream>>>(map, p);
+    return SN_OK;
 }
 
 // in: blk (n_pc, P, Cin_pad/8, S^3, 8).  EPI_BLK: out blk with cg_out_total groups, written at cg_out_off.
@@ -544,22 +634,25 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
     TcState* st = (TcState*)net.tc;
     const ConvUnit& cu = net.units[u];
     const TcUnit& tu = st->units[u];
+    const TcVariant& tv = tu.v[(P == 2) ? 0 : 1];
     int rc = get_encode(st);
     if (rc != SN_OK) return rc;
-    const TileCfg cfg = tile_cfg(cu, tu, S, P);
+    const TileCfg cfg = tile_cfg(cu, tv, S, P);
     ConvTcParams p{};
     p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.n_cblk = tu.Cin_pad / 16; p.cg_in = tu.Cin_pad / 8;
-    p.P = P; p.AD = cfg.AD; p.NB = cfg.NB;
+    p.NB = cfg.NB;
+    const int AD = cfg.AD;
     const int pad = cu.dil * (cu.K / 2);
-    p.PW = TC_TW + 2 * pad; p.HH = TC_TH + 2 * pad; p.HD = p.AD + 2 * pad;
+    p.PW = TC_TW + 2 * pad; p.HH = TC_TH + 2 * pad; p.HD = AD + 2 * pad;
     p.a_prec_bytes = p.PW * p.HH * p.HD * 32;
-    p.tiles_w = (int)cdiv(S, TC_TW); p.tiles_h = (int)cdiv(S, TC_TH); p.tiles_d = (int)cdiv(S, p.AD);
-    p.n_ntiles = tu.n_ntiles;
-    const int variant = (P == 2) ? 0 : 1;
-    for (int t = 0; t < 2; ++t) { p.nt_size[t] = tu.nt_size[t]; p.nt_off[t] = tu.nt_off[t]; p.nt_woff[t] = tu.nt_woff[variant][t]; }
-    p.weights = tu.w[variant]; p.scale = tu.scale; p.shift = tu.shift; p.act = cu.act; p.epi = epi;
+    p.tiles_w = (int)cdiv(S, TC_TW); p.tiles_h = (int)cdiv(S, TC_TH); p.tiles_d = (int)cdiv(S, AD);
+    p.n_ntiles = tv.n_ntiles;
+    int Nmax = 0;
+    for (int t = 0; t < TC_MAX_NT; ++t) { p.nt_size[t] = tv.nt_size[t]; p.nt_off[t] = tv.nt_off[t]; p.nt_woff[t] = tv.nt_woff[t]; Nmax = std::max(Nmax, tv.nt_size[t]); }
+    p.weights = tv.w; p.scale = tu.scale; p.shift = tu.shift; p.act = cu.act; p.epi = epi;
     p.out = out; p.cg_out_total = cg_out_total; p.cg_out_off = cg_out_off;
     p.w3 = st->w3; p.scale3 = st->scale3; p.shift3 = st->shift3; p.c3 = net.units[U_MERGE3].Cin; p.prob_out = prob_out;
+    SN_CHECK_ARG(epi != EPI_FINAL || tv.n_ntiles == 1, "conv_tc: the fused merge_conv3 epilogue needs all channels in one N tile");
 
     CUtensorMap map;
     const cuuint64_t gdim[4] = {(cuuint64_t)8 * S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)n_pc * P * p.cg_in};
@@ -570,18 +663,16 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for unit %s, S=%d", (int)cr, kUnits[u].name, S); return SN_ERR_CUDA; }
 
-    const int Nmax = std::max(tu.nt_size[0], tu.nt_size[1]);
     const size_t smem = 2 * (size_t)p.a_prec_bytes * P + (size_t)p.NB * Nmax * 32 * P + (5 + 2 * p.NB) * 8 + 16;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        SN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_smem = 227 * 1024;
-    }
     const long long tiles = (long long)n_pc * p.tiles_d * p.tiles_h * p.tiles_w;
-    SN_CHECK_ARG(tiles <= 0x7fffffff && smem <= 227 * 1024, "conv_tc: launch too large (tiles=%lld smem=%zu)", tiles, smem);
-    dim3 grid((unsigned)tiles, (unsigned)tu.n_ntiles);
+    SN_CHECK_ARG(tiles <= 0x7fffffff && smem <= 227 * 1024 && AD * P * Nmax <= 512, "conv_tc: launch too large (tiles=%lld smem=%zu)", tiles, smem);
+    dim3 grid((unsigned)tiles, (unsigned)tv.n_ntiles);
     prof_begin(u, stream);
-    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(map, p);
+#define SN_TC_CASE(a, pp) if (AD == a && P == pp) rc = conv_tc_launch_t<a, pp>(map, p, grid, smem, stream)
+    SN_TC_CASE(1, 1); SN_TC_CASE(2, 1); SN_TC_CASE(3, 1); SN_TC_CASE(4, 1);
+    SN_TC_CASE(1, 2); SN_TC_CASE(2, 2); SN_TC_CASE(3, 2); SN_TC_CASE(4, 2);
+#undef SN_TC_CASE
+    if (rc != SN_OK) return rc;
     prof_end(u, stream);
     SN_LAUNCHED();
     return SN_OK;

@@ -222,6 +222,7 @@ def run_gpu(args, wl):
         _lib.lib.sn_launch_count_reset()
         if profile:
             _lib.lib.sn_profile_enable(1)
+            torch.cuda.cudart().cudaProfilerStart()      # ncu --profile-from-start off captures the timed region only
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t0 = time.time()
         for a, b in evs:
@@ -232,6 +233,8 @@ def run_gpu(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
         t1 = time.time()
+        if profile:
+            torch.cuda.cudart().cudaProfilerStop()
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -257,7 +260,20 @@ def run_gpu(args, wl):
         conv_ms = sum(ms_u[i] for i in range(n_units))
         conv_launches = sum(cnt_u[i] for i in range(n_units))
         conv_flop_step = 2.0 * sum(macs) * pair_vox_step
-        achieved = conv_flop_step * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        conv_tflops = conv_flop_step * args.steps / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        # dominant kernel = the merge_conv2 launch of conv_tc_kernel (3x3x3, 100->100, + fused merge_conv3 + sigmoid epilogue)
+        names = [u[0] for u in weights.UNITS]
+        dom = names.index("merge_conv2")
+        dom_flop_launch = 2.0 * (macs[dom] + macs[names.index("merge_conv3")]) * pair_vox_step * args.steps / max(cnt_u[dom], 1)
+        dom_ms_launch = ms_u[dom] / max(cnt_u[dom], 1)
+        achieved = dom_flop_launch / (dom_ms_launch * 1e-3) / 1e12 if dom_ms_launch > 0 else 0.0
+        traffic = None
+        summ = os.path.join(REPO, "profiles", "ncu_summary.json")
+        if os.path.exists(summ):
+            try:
+                traffic = json.load(open(summ)).get(mode, {}).get("merge_conv2", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         per_unit = {weights.UNITS[i][0]: {"ms_per_step": ms_u[i] / args.steps, "tflops": (2.0 * macs[i] * pair_vox_step * args.steps / (ms_u[i] * 1e-3) / 1e12) if ms_u[i] > 0 else 0.0}
                     for i in range(n_units) if cnt_u[i]}
         fused_vox = world * B * V
@@ -277,9 +293,14 @@ def run_gpu(args, wl):
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "3D conv units (%d launches/step)" % (conv_launches // args.steps), "achieved": achieved,
-                         "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src,
-                         "conv_share_of_step": conv_ms / args.steps / ms_dev, "per_unit": per_unit},
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel, merge_conv2 launch (3x3x3 100->100 + fused merge_conv3/sigmoid), %d launches/step" % (cnt_u[dom] // args.steps),
+                         "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": traffic,
+                         "peak_source": peak_src, "flop_per_launch": dom_flop_launch, "ms_per_launch": dom_ms_launch,
+                         "kernel_share_of_step": ms_u[dom] / args.steps / ms_dev,
+                         "all_conv_units": {"launches_per_step": conv_launches // args.steps, "tflops": conv_tflops, "frac": conv_tflops / tc_peak,
+                                            "share_of_step": conv_ms / args.steps / ms_dev},
+                         "exact_mode_ceiling_frac": (1.0 / 3.0) * (100.0 / 112.0) ** 2 if mode in ("exact", "tc_exact") else None,
+                         "per_unit": per_unit},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsurfacenet_b200.so")
 
 SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_DOMAIN, SN_ERR_NOMEM = 0, -1, -2, -3, -4
 MODE_FP32, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2
-DEFAULT_MODE = os.environ.get("SN_MODE", "fp32")      # the mode bench.py / smoke() run unless told otherwise
+DEFAULT_MODE = os.environ.get("SN_MODE", "exact")      # the mode bench.py / smoke() run unless told otherwise
 MODES = {"fp32": MODE_FP32, "exact": MODE_TC_EXACT, "tc_exact": MODE_TC_EXACT, "fast": MODE_TC_FAST, "tc_fast": MODE_TC_FAST}
 
 if not os.path.exists(LIB_PATH):

@@ -598,8 +598,30 @@ void tc_destroy(Net& net) {
     net.tc = nullptr;
 }
 
+// optional persistence of the measured tile configurations (SN_TC_TUNE_FILE): lets a profiler run reuse the table of a
+// previous run instead of re-measuring inside the profiled region
+static void tune_file_load(TcState* st) {
+    const char* path = getenv("SN_TC_TUNE_FILE");
+    if (!path) return;
+    FILE* f = fopen(path, "r");
+    if (!f) return;
+    int key, ad, nb; long long work;
+    while (fscanf(f, "%d %d %d %lld", &key, &ad, &nb, &work) == 4)
+        if (ad >= 1 && ad <= 4 && nb >= 2 && nb <= 16) st->tuned[key] = std::make_pair(TileCfg{ad, nb}, work);
+    fclose(f);
+}
+static void tune_file_save(const TcState* st) {
+    const char* path = getenv("SN_TC_TUNE_FILE");
+    if (!path) return;
+    FILE* f = fopen(path, "w");
+    if (!f) return;
+    for (const auto& kv : st->tuned) fprintf(f, "%d %d %d %lld\n", kv.first, kv.second.first.AD, kv.second.first.NB, kv.second.second);
+    fclose(f);
+}
+
 static int get_encode(TcState* st) {
     if (st->encode) return SN_OK;
+    tune_file_load(st);
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     SN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -737,6 +759,7 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
             if (getenv("SN_TC_VERBOSE")) fprintf(stderr, "[surfacenet_b200] tuned %s S=%d P=%d n=%d: AD=%d NB=%d (%.3f ms)\n", kUnits[u].name, S, P, n_pc, cfg.AD, cfg.NB, best / 2);
         }
         st->tuned[key] = std::make_pair(cfg, work);
+        tune_file_save(st);
     }
     prof_begin(u, stream);
     rc = conv_tc_launch_cfg(args, cfg, stream);

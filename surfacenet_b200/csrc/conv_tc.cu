@@ -107,7 +107,8 @@ constexpr int EPI_BLK = 0, EPI_FINAL = 1;
 constexpr int TC_MAX_NT = 4;
 
 struct ConvTcParams {
-    int S, n_pc, dil, K, taps, n_cblk, cg_in, NB;
+    int S, n_pc, dil, K, taps, n_cblk, cg_in, NB, nbuf;
+    long long n_tiles;              // tiles_w * tiles_h * tiles_d * n_pc * n_ntiles
     int PW, HH, HD;                 // halo tile extents (voxels)
     int a_prec_bytes;               // bytes of one precision plane of one A stage = PW*HH*HD*32
     int tiles_w, tiles_h, tiles_d;
@@ -151,39 +152,55 @@ __device__ __forceinline__ bool elect_one() {
 // main one receives only A_hi*W_hi, the correction one A_lo*W_hi + A_hi*W_lo (2^-11 smaller).  tcgen05
 // truncates (round-toward-zero) once per accumulating MMA, a bias that grows linearly with the number of
 // MMAs into an accumulator; keeping the small terms out of the big accumulator divides that bias by three.
+//
+// The kernel is PERSISTENT: gridDim.x CTAs walk the tile list with stride gridDim.x.  Barriers, TMEM and the
+// tensor map are set up once; the producer warps run ahead into the next tile while the MMA warp finishes the
+// current one, and with two TMEM accumulator sets (nbuf = 2, when 2*AD*P*N <= 512 columns) the epilogue of
+// tile j overlaps the main loop of tile j+1.
+struct TileCoord { int nt, pc, d0, h0, w0; };
+
+template <int AD>
+__device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, uint32_t t) {
+    TileCoord c;
+    uint32_t q = t / (uint32_t)p.tiles_w; c.w0 = (int)(t - q * p.tiles_w) * TC_TW; t = q;
+    q = t / (uint32_t)p.tiles_h; c.h0 = (int)(t - q * p.tiles_h) * TC_TH; t = q;
+    q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * AD; t = q;
+    q = t / (uint32_t)p.n_pc; c.pc = (int)(t - q * p.n_pc);
+    c.nt = (int)q;
+    return c;
+}
+
+// co-resident CTAs the register allocation must allow: small fast-mode CTAs share an SM four at a time
+template <int AD, int P> struct TcMinBlocks { static constexpr int value = (P == 1) ? (AD == 1 ? 4 : (AD == 2 ? 2 : 1)) : (AD == 1 ? 2 : 1); };
+
 template <int AD, int P>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, TcMinBlocks<AD, P>::value)
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NB = p.NB;
-    const int nt = blockIdx.y;
-    const int N = p.nt_size[nt];
+    const int Nmax = p.nt_size[0];                                    // N tiles are sorted largest first
     const uint32_t a_stage_bytes = (uint32_t)p.a_prec_bytes * P;
-    const uint32_t b_prec_bytes = (uint32_t)N * 32;
-    const uint32_t b_stage_bytes = b_prec_bytes * P;
+    const uint32_t b_slot_bytes = (uint32_t)Nmax * 32 * P;            // ring slot, sized for the largest N tile
     unsigned char* smA = smem;                                        // [2][P][2 groups][HD][HH][PW][8] fp16
-    unsigned char* smB = smem + 2 * a_stage_bytes;                    // [NB][P][2][N/8][8][8] fp16
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)NB * b_stage_bytes);
-    uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + NB, *acc_full = bars + 4 + 2 * NB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * NB);
-
-    // tile -> (pair-cube, d0, h0, w0)
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h; t /= p.tiles_h;
-    const int td = t % p.tiles_d; t /= p.tiles_d;
-    const int pc = t;
-    const int w0 = tw * TC_TW, h0 = th * TC_TH, d0 = td * AD;
+    unsigned char* smB = smem + 2 * a_stage_bytes;                    // [NB][2][P][N/8][8][8] fp16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)NB * b_slot_bytes);
+    uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + NB;
+    uint64_t* acc_full = bars + 4 + 2 * NB, *acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int pad = p.dil * (p.K / 2);
-
+    const int nbuf = p.nbuf;
+    const uint32_t buf_cols = (uint32_t)(AD * P * Nmax);
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < AD * P * N) tmem_cols <<= 1;
+    while (tmem_cols < buf_cols * nbuf) tmem_cols <<= 1;
+    const uint32_t n_tiles = (uint32_t)p.n_tiles;
 
+    // two MMA-issuing warps (2 and 3) when there are >= 2 planes: each owns the planes a with a % 2 == its index, which
+    // doubles the rate at which tcgen05.mma instructions can be handed to the tensor pipe
+    constexpr int NI = (AD >= 2) ? 2 : 1;
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], NI); mbar_init(&acc_full[i], NI); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
     }
@@ -198,149 +215,179 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
 
     if (warp == 0) {
         // ===== A producer: one zero-padded halo tile of 16 channels (x P precisions) per channel block =====
-        for (int cb = 0; cb < p.n_cblk; ++cb) {
-            const int s = cb & 1;
-            mbar_wait(&a_empty[s], ((cb >> 1) & 1) ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(&a_full[s], a_stage_bytes);
+        uint32_t ia = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileCoord c = tile_coord<AD>(p, t);
+            for (int cb = 0; cb < p.n_cblk; ++cb, ++ia) {
+                const int s = ia & 1;
+                mbar_wait(&a_empty[s], ((ia >> 1) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[s], a_stage_bytes);
 #pragma unroll
-                for (int pr = 0; pr < P; ++pr)
-                    tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
-                                8 * (w0 - pad), h0 - pad, d0 - pad, (pc * P + pr) * p.cg_in + 2 * cb);
+                    for (int pr = 0; pr < P; ++pr)
+                        tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
+                                    8 * (c.w0 - pad), c.h0 - pad, c.d0 - pad, (c.pc * P + pr) * p.cg_in + 2 * cb);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == 1) {
         // ===== B producer: the (channel block, tap) weight tile, already in canonical layout in HBM =====
-        const unsigned char* wsrc = p.weights + p.nt_woff[nt];
         const int total = p.n_cblk * p.taps;
         int s = 0; uint32_t ph = 0;
-        for (int it = 0; it < total; ++it) {
-            mbar_wait(&b_empty[s], ph ^ 1);
-            if (elect_one()) {
-                mbar_expect_tx(&b_full[s], b_stage_bytes);
-                bulk_load(smB + (size_t)s * b_stage_bytes, wsrc + (size_t)it * b_stage_bytes, b_stage_bytes, &b_full[s]);
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const TileCoord c = tile_coord<AD>(p, t);
+            const uint32_t stage_bytes = (uint32_t)p.nt_size[c.nt] * 32 * P;
+            const unsigned char* wsrc = p.weights + p.nt_woff[c.nt];
+            for (int it = 0; it < total; ++it) {
+                mbar_wait(&b_empty[s], ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&b_full[s], stage_bytes);
+                    bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * stage_bytes, stage_bytes, &b_full[s]);
+                }
+                __syncwarp();
+                if (++s == NB) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
-            if (++s == NB) { s = 0; ph ^= 1; }
         }
-    } else if (warp == 2) {
-        // ===== MMA issuer: the warp stays converged, one elected lane issues =====
+    } else if (warp == 2 || (warp == 3 && NI == 2)) {
+        // ===== MMA issuer(s): the warp stays converged, one elected lane issues =====
+        const int me = warp - 2;
         // exact mode, per (tap, plane):  [main | corr] (N' = 2N columns) += A_hi * [W_hi ; W_lo]^T      (one N' = 2N MMA)
         //                                         corr  (N columns)      += A_lo * W_hi^T
         // i.e. the three products of the hi/lo split in two MMAs, A_hi fetched from shared memory once.
-        const uint32_t idesc1 = (1u << 4) | ((uint32_t)((P * N) >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, M=128
-        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         // descriptor words (units of 16 B): hi = SBO | version 1, lo = start | LBO << 16
         const uint32_t a_hi32 = (uint32_t)p.PW | (1u << 14);
         const uint32_t b_hi32 = 8u | (1u << 14);
         const uint32_t a_lbo = (uint32_t)(p.a_prec_bytes >> 5) << 16;        // one channel-group plane of the halo tile
-        const uint32_t b_lbo = (uint32_t)(P * N) << 16;                      // one K half of the stage: P*N rows of 16 B
         const uint32_t smA16 = smem_u32(smA) >> 4, smB16 = smem_u32(smB) >> 4;
         const uint32_t a_stage16 = a_stage_bytes >> 4, a_prec16 = (uint32_t)p.a_prec_bytes >> 4;
-        const uint32_t b_stage16 = b_stage_bytes >> 4;
+        const uint32_t b_slot16 = b_slot_bytes >> 4;
         const uint32_t plane16 = (uint32_t)(p.HH * p.PW), row16 = (uint32_t)p.PW;
         const uint32_t dil = (uint32_t)p.dil;
-        int sb = 0; uint32_t phb = 0, acc_flag = 0;
-        for (int cb = 0; cb < p.n_cblk; ++cb) {
-            const int sa = cb & 1;
-            mbar_wait(&a_full[sa], (cb >> 1) & 1);
+        int sb = 0; uint32_t phb = 0, ia = 0, j = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const TileCoord c = tile_coord<AD>(p, t);
+            const int N = p.nt_size[c.nt];
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)((P * N) >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, M=128
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_lbo = (uint32_t)(P * N) << 16;                  // one K half of the stage: P*N rows of 16 B
+            const uint32_t buf = (nbuf == 2) ? (j & 1) : 0;
+            const uint32_t use = (nbuf == 2) ? (j >> 1) : j;                 // how often this accumulator set was used before
+            const uint32_t dbase = tmem_base + buf * buf_cols;
+            mbar_wait(&acc_empty[buf], (use & 1) ^ 1);                       // epilogue has drained the previous tile of this set
             tc_fence_after();
-            const uint32_t a_lo32 = (smA16 + sa * a_stage16) | a_lbo;
-            for (int kd = 0; kd < p.K; ++kd)
-                for (int kh = 0; kh < p.K; ++kh)
-                    for (int kw = 0; kw < p.K; ++kw) {
-                        const uint32_t tap16 = (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
-                        mbar_wait(&b_full[sb], phb);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t db = ((uint64_t)b_hi32 << 32) | ((smB16 + sb * b_stage16) | b_lbo);
-#pragma unroll
-                            for (int a = 0; a < AD; ++a) {
-                                const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (a_lo32 + tap16 + a * plane16);
-                                tc_mma(tmem_base + (uint32_t)(a * P * N), da_hi, db, idesc1, acc_flag);
-                            }
-                            if (P == 2) {
+            uint32_t acc_flag = 0;
+            for (int cb = 0; cb < p.n_cblk; ++cb, ++ia) {
+                const int sa = ia & 1;
+                mbar_wait(&a_full[sa], (ia >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_lo32 = (smA16 + sa * a_stage16) | a_lbo;
+                for (int kd = 0; kd < p.K; ++kd)
+                    for (int kh = 0; kh < p.K; ++kh)
+                        for (int kw = 0; kw < p.K; ++kw) {
+                            const uint32_t tap16 = (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
+                            mbar_wait(&b_full[sb], phb);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t db = ((uint64_t)b_hi32 << 32) | ((smB16 + sb * b_slot16) | b_lbo);
 #pragma unroll
                                 for (int a = 0; a < AD; ++a) {
-                                    const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (a_lo32 + a_prec16 + tap16 + a * plane16);
-                                    tc_mma(tmem_base + (uint32_t)(a * P * N + N), da_lo, db, idesc2, 1u);
+                                    if (NI == 2 && (a & 1) != me) continue;
+                                    const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (a_lo32 + tap16 + a * plane16);
+                                    tc_mma(dbase + (uint32_t)(a * P * N), da_hi, db, idesc1, acc_flag);
                                 }
+                                if (P == 2) {
+#pragma unroll
+                                    for (int a = 0; a < AD; ++a) {
+                                        if (NI == 2 && (a & 1) != me) continue;
+                                        const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (a_lo32 + a_prec16 + tap16 + a * plane16);
+                                        tc_mma(dbase + (uint32_t)(a * P * N + N), da_lo, db, idesc2, 1u);
+                                    }
+                                }
+                                tc_commit(&b_empty[sb]);              // weight slot free once these MMAs retire
                             }
-                            tc_commit(&b_empty[sb]);              // weight stage free once these MMAs retire
+                            __syncwarp();
+                            acc_flag = 1u;
+                            if (++sb == NB) { sb = 0; phb ^= 1; }
                         }
-                        __syncwarp();
-                        acc_flag = 1u;
-                        if (++sb == NB) { sb = 0; phb ^= 1; }
-                    }
-            if (elect_one()) tc_commit(&a_empty[sa]);
+                if (elect_one()) tc_commit(&a_empty[sa]);
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(&acc_full[buf]);
             __syncwarp();
         }
-        if (elect_one()) tc_commit(acc_full);
-        __syncwarp();
     } else if (warp >= 4) {
         // ===== epilogue: TMEM lane quarter (warp % 4) -> rows m = 32 q + lane -> voxel (h0 + m/8, w0 + m%8) =====
-        mbar_wait_sleep(acc_full, 0);
-        tc_fence_after();
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        const int h = h0 + (m >> 3), w = w0 + (m & 7);
         const int S = p.S;
         const long long vol = (long long)S * S * S;
-        const int c_base = p.nt_off[nt];
+        uint32_t j = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const TileCoord c = tile_coord<AD>(p, t);
+            const int N = p.nt_size[c.nt];
+            const int c_base = p.nt_off[c.nt];
+            const int h = c.h0 + (m >> 3), w = c.w0 + (m & 7);
+            const uint32_t buf = (nbuf == 2) ? (j & 1) : 0;
+            const uint32_t use = (nbuf == 2) ? (j >> 1) : j;
+            mbar_wait_sleep(&acc_full[buf], use & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int a = 0; a < AD; ++a) {
-            const int d = d0 + a;
-            const bool ok = (d < S) && (h < S) && (w < S);             // warp-uniform loads, predicated stores
-            const long long vox = ((long long)d * S + h) * S + w;
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P * N);
-            float z = 0.f;
+            for (int a = 0; a < AD; ++a) {
+                const int d = c.d0 + a;
+                const bool ok = (d < S) && (h < S) && (w < S);             // warp-uniform loads, predicated stores
+                const long long vox = ((long long)d * S + h) * S + w;
+                const uint32_t trow = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P * N);
+                float z = 0.f;
 #pragma unroll 1
-            for (int j = 0; j < N; j += 16) {
-                uint32_t v[16];
-                tc_ld16(trow + j, v);
-                if (P == 2) {
-                    uint32_t c[16];
-                    tc_ld16(trow + (uint32_t)N + j, c);
-                    tc_ld_wait();
+                for (int jc = 0; jc < N; jc += 16) {
+                    uint32_t v[16];
+                    tc_ld16(trow + jc, v);
+                    if (P == 2) {
+                        uint32_t cc[16];
+                        tc_ld16(trow + (uint32_t)N + jc, cc);
+                        tc_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
-                } else {
-                    tc_ld_wait();
-                }
-                float y[16];
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cc[i]));
+                    } else {
+                        tc_ld_wait();
+                    }
+                    float y[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = c_base + j + i;
-                    y[i] = tc_act(fmaf(__uint_as_float(v[i]), __ldg(p.scale + c), __ldg(p.shift + c)), p.act);
-                }
-                if (p.epi == EPI_FINAL) {
+                    for (int i = 0; i < 16; ++i) {
+                        const int ch = c_base + jc + i;
+                        y[i] = tc_act(fmaf(__uint_as_float(v[i]), __ldg(p.scale + ch), __ldg(p.shift + ch)), p.act);
+                    }
+                    if (p.epi == EPI_FINAL) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (j + i < p.c3) z = fmaf(y[i], __ldg(p.w3 + j + i), z);
-                } else if (ok) {
+                        for (int i = 0; i < 16; ++i)
+                            if (jc + i < p.c3) z = fmaf(y[i], __ldg(p.w3 + jc + i), z);
+                    } else if (ok) {
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        __half hi[8], lo[8];
+                        for (int g = 0; g < 2; ++g) {
+                            __half hi[8], lo[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            hi[i] = __float2half_rn(y[8 * g + i]);
-                            lo[i] = __float2half_rn(y[8 * g + i] - __half2float(hi[i]));
+                            for (int i = 0; i < 8; ++i) {
+                                hi[i] = __float2half_rn(y[8 * g + i]);
+                                lo[i] = __float2half_rn(y[8 * g + i] - __half2float(hi[i]));
+                            }
+                            const int cg = p.cg_out_off + ((c_base + jc) >> 3) + g;
+                            __half* dst = p.out + (((long long)c.pc * P) * p.cg_out_total + cg) * vol * 8 + vox * 8;
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+                            if (P == 2)
+                                *reinterpret_cast<uint4*>(dst + (long long)p.cg_out_total * vol * 8) =
+                                    make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
                         }
-                        const int cg = p.cg_out_off + ((c_base + j) >> 3) + g;
-                        __half* dst = p.out + (((long long)pc * P) * p.cg_out_total + cg) * vol * 8 + vox * 8;
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-                        if (P == 2)
-                            *reinterpret_cast<uint4*>(dst + (long long)p.cg_out_total * vol * 8) =
-                                make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
                     }
                 }
+                if (p.epi == EPI_FINAL && ok)
+                    p.prob_out[(long long)c.pc * vol + vox] = 1.f / (1.f + expf(-fmaf(z, p.scale3, p.shift3)));
             }
-            if (p.epi == EPI_FINAL && ok)
-                p.prob_out[(long long)pc * vol + vox] = 1.f / (1.f + expf(-fmaf(z, p.scale3, p.shift3)));
+            tc_fence_before();                                             // TMEM reads done -> the MMA warp may overwrite this set
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 3) {
         tc_fence_after();
@@ -442,50 +489,60 @@ __global__ void pool_blk_kernel(const __half* __restrict__ in, int cg, int P, in
     }
 }
 
-// zero-stuff by f + fixed k^3 conv ('same'), blk (cg_in groups at S) -> groups [cg_off, cg_off + cg_in) of a blk
-// tensor with cg_total groups at f*S                                          nets/layers.py:376-390, SurfaceNet.py:71
-__global__ void upsample_blk_kernel(const __half* __restrict__ in, const float* __restrict__ W, int k, int f, int cg_in, int P, int S,
-                                    long long total, __half* __restrict__ out, int cg_total, int cg_off) {
-    const int So = S * f, c0 = k / 2;
+// zero-stuff by F + fixed K^3 conv ('same'), blk (cg_in groups at S) -> groups [cg_off, cg_off + cg_in) of a blk
+// tensor with cg_total groups at F*S                                          nets/layers.py:376-390, SurfaceNet.py:71
+// out[o] = sum_t W[t] * stuffed[o + t - K/2], stuffed[p] = in[p/F] when p % F == 0 in all three dims: per dimension only
+// the taps t = t0, t0+F, ... with t0 = (K/2 - o) mod F are non-zero (<= ceil(K/F) of them).
+// grid = (ceil(So^2 / 256), So, n * cg_in): one thread per output voxel of one 8-channel group; HBM-write bound.
+template <int F, int K>
+__global__ void __launch_bounds__(256)
+upsample_blk_kernel(const __half* __restrict__ in, const float* __restrict__ W, int cg_in, int P, int S,
+                    __half* __restrict__ out, int cg_total, int cg_off) {
+    constexpr int C0 = K / 2, NT = (K + F - 1) / F;
+    __shared__ float sW[K * K * K];
+    for (int i = threadIdx.x; i < K * K * K; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    const int So = S * F;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= So * So) return;
+    const int oh = idx / So, ow = idx - oh * So, od = blockIdx.y;
+    const int g = blockIdx.z % cg_in;
+    const long long n = blockIdx.z / cg_in;
     const long long vol = (long long)S * S * S, volo = (long long)So * So * So;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        const int ow = (int)(i % So), oh = (int)((i / So) % So), od = (int)((i / ((long long)So * So)) % So);
-        const int g = (int)((i / volo) % cg_in);
-        const long long n = i / (volo * cg_in);
-        const __half* base = in + ((n * P) * cg_in + g) * vol * 8;
-        const int td0 = ((c0 - od) % f + f) % f, th0 = ((c0 - oh) % f + f) % f, tw0 = ((c0 - ow) % f + f) % f;
-        float acc[8];
+    const __half* base = in + ((n * P) * cg_in + g) * vol * 8;
+    const int td0 = (C0 - od) & (F - 1), th0 = (C0 - oh) & (F - 1), tw0 = (C0 - ow) & (F - 1);
+    float acc[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-        for (int td = td0; td < k; td += f) {
-            const int pd = od + td - c0;
-            if (pd < 0 || pd >= So) continue;
-            for (int th = th0; th < k; th += f) {
-                const int ph = oh + th - c0;
-                if (ph < 0 || ph >= So) continue;
-                for (int tw = tw0; tw < k; tw += f) {
-                    const int pw = ow + tw - c0;
-                    if (pw < 0 || pw >= So) continue;
-                    const float wt = __ldg(W + (td * k + th) * k + tw);
-                    float v[8];
-                    load_blk8(base + (((long long)(pd / f) * S + ph / f) * S + pw / f) * 8, (long long)cg_in * vol * 8, P, v);
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[q] = fmaf(wt, v[q], acc[q]);
-                }
+    for (int jd = 0; jd < NT; ++jd) {
+        const int td = td0 + jd * F, pd = od + td - C0;
+        if (td >= K || pd < 0 || pd >= So) continue;
+#pragma unroll
+        for (int jh = 0; jh < NT; ++jh) {
+            const int th = th0 + jh * F, ph = oh + th - C0;
+            if (th >= K || ph < 0 || ph >= So) continue;
+#pragma unroll
+            for (int jw = 0; jw < NT; ++jw) {
+                const int tw = tw0 + jw * F, pw = ow + tw - C0;
+                if (tw >= K || pw < 0 || pw >= So) continue;
+                const float wt = sW[(td * K + th) * K + tw];
+                float v[8];
+                load_blk8(base + (((long long)(pd / F) * S + ph / F) * S + pw / F) * 8, (long long)cg_in * vol * 8, P, v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = fmaf(wt, v[q], acc[q]);
             }
         }
-        store_blk8(out + ((n * P) * cg_total + cg_off + g) * volo * 8 + (((long long)od * So + oh) * So + ow) * 8,
-                   (long long)cg_total * volo * 8, P, acc);
     }
+    store_blk8(out + ((n * P) * cg_total + cg_off + g) * volo * 8 + (((long long)od * So + oh) * So + ow) * 8,
+               (long long)cg_total * volo * 8, P, acc);
 }
 
 static inline int ew_blocks(long long total) { return (int)std::min<long long>(cdiv(total, 256), 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
 // host side: weight preparation, tensor maps, launches
-struct TileCfg { int AD, NB; };                   // d-planes per CTA, weight-ring depth
+struct TileCfg { int AD, NB, persist; };          // d-planes per CTA, weight-ring depth, persistent CTAs (1) or one CTA per tile (0)
 struct TcVariant {                                 // [0] exact (P = 2), [1] fast (P = 1): own N tiling and weight image
     int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0};
     long long nt_woff[TC_MAX_NT] = {0, 0, 0, 0};
@@ -607,7 +664,7 @@ static void tune_file_load(TcState* st) {
     if (!f) return;
     int key, ad, nb; long long work;
     while (fscanf(f, "%d %d %d %lld", &key, &ad, &nb, &work) == 4)
-        if (ad >= 1 && ad <= 4 && nb >= 2 && nb <= 16) st->tuned[key] = std::make_pair(TileCfg{ad, nb}, work);
+        if ((ad % 8) >= 1 && (ad % 8) <= 4 && nb >= 2 && nb <= 16) st->tuned[key] = std::make_pair(TileCfg{ad % 8, nb, ad / 8}, work);
     fclose(f);
 }
 static void tune_file_save(const TcState* st) {
@@ -615,7 +672,7 @@ static void tune_file_save(const TcState* st) {
     if (!path) return;
     FILE* f = fopen(path, "w");
     if (!f) return;
-    for (const auto& kv : st->tuned) fprintf(f, "%d %d %d %lld\n", kv.first, kv.second.first.AD, kv.second.first.NB, kv.second.second);
+    for (const auto& kv : st->tuned) fprintf(f, "%d %d %d %lld\n", kv.first, kv.second.first.AD + 8 * kv.second.first.persist, kv.second.first.NB, kv.second.second);
     fclose(f);
 }
 
@@ -633,7 +690,7 @@ static int get_encode(TcState* st) {
 static size_t tc_smem_bytes(const ConvUnit& cu, int Nmax, int P, TileCfg c) {
     const int pad = cu.dil * (cu.K / 2);
     const int PW = TC_TW + 2 * pad, HH = TC_TH + 2 * pad;
-    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P + (5 + 2 * c.NB) * 8 + 16;
+    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P + (8 + 2 * c.NB) * 8 + 16;
 }
 
 // feasible (d-planes per CTA, weight-ring depth) pairs: <= 512 TMEM columns (P accumulators per plane), <= 227 KB smem.
@@ -647,12 +704,12 @@ static std::vector<TileCfg> tile_candidates(const ConvUnit& cu, int Nmax, int S,
     std::vector<TileCfg> out;
     for (int ad = 1; ad <= ADmax; ++ad) {
         if ((double)S / (double)(cdiv(S, ad) * ad) < 0.85 && ad > 1) continue;       // too many planes outside the volume
-        for (int nb : {2, 3, 4, 6, 8}) {
+        for (int nb : {3, 6}) {
             if (env_nb && nb != env_nb) continue;
-            if (tc_smem_bytes(cu, Nmax, P, {ad, nb}) <= 227 * 1024) out.push_back({ad, nb});
+            if (tc_smem_bytes(cu, Nmax, P, {ad, nb, 0}) <= 227 * 1024) { out.push_back({ad, nb, 0}); out.push_back({ad, nb, 1}); }
         }
     }
-    if (out.empty()) out.push_back({1, 2});
+    if (out.empty()) out.push_back({1, 2, 1});
     return out;
 }
 
@@ -702,11 +759,23 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for unit %s, S=%d", (int)cr, kUnits[a.u].name, S); return SN_ERR_CUDA; }
 
     const size_t smem = tc_smem_bytes(cu, Nmax, P, cfg);
-    const long long tiles = (long long)a.n_pc * p.tiles_d * p.tiles_h * p.tiles_w;
-    SN_CHECK_ARG(tiles <= 0x7fffffff && smem <= 227 * 1024 && AD * P * Nmax <= 512, "conv_tc: launch too large (tiles=%lld smem=%zu)", tiles, smem);
-    dim3 grid((unsigned)tiles, (unsigned)tv.n_ntiles);
+    p.n_tiles = (long long)a.n_pc * p.tiles_d * p.tiles_h * p.tiles_w * tv.n_ntiles;
+    p.nbuf = (cfg.persist && 2 * AD * P * Nmax <= 512) ? 2 : 1;
+    SN_CHECK_ARG(smem <= 227 * 1024 && AD * P * Nmax <= 512 && Nmax == tv.nt_size[0], "conv_tc: bad tile configuration (smem=%zu)", smem);
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; SN_CUDA(cudaGetDevice(&dev)); SN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    // persistent CTAs per SM: bounded by shared memory and by TMEM columns (allocations are powers of two >= 32).  The
+    // block scheduler does not know about TMEM, so the dynamic smem request is padded until no more than `per_sm`
+    // CTAs fit: an extra CTA would otherwise sit in tcgen05.alloc until a resident one has finished all its tiles.
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(p.nbuf * AD * P * Nmax)) cols <<= 1;
+    static const int env_occ = getenv("SN_TC_OCC") ? atoi(getenv("SN_TC_OCC")) : 8;
+    const int per_sm = std::max(1, std::min(std::min((int)(227 * 1024 / (smem + 1024)), (int)(512 / cols)), env_occ));
+    const size_t smem_launch = cfg.persist ? std::max(smem, (size_t)(227 * 1024 / (per_sm + 1)) + 1) : smem;
+    SN_CHECK_ARG(p.n_tiles <= 0x7fffffff, "conv_tc: too many tiles (%lld)", p.n_tiles);
+    dim3 grid((unsigned)(cfg.persist ? std::min<long long>(p.n_tiles, (long long)n_sm * per_sm) : p.n_tiles));
     int rc = SN_ERR_INVALID;
-#define SN_TC_CASE(ad, pp) if (AD == ad && P == pp) rc = conv_tc_launch_t<ad, pp>(map, p, grid, smem, stream)
+#define SN_TC_CASE(ad, pp) if (AD == ad && P == pp) rc = conv_tc_launch_t<ad, pp>(map, p, grid, smem_launch, stream)
     SN_TC_CASE(1, 1); SN_TC_CASE(2, 1); SN_TC_CASE(3, 1); SN_TC_CASE(4, 1);
     SN_TC_CASE(1, 2); SN_TC_CASE(2, 2); SN_TC_CASE(3, 2); SN_TC_CASE(4, 2);
 #undef SN_TC_CASE
@@ -756,7 +825,7 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
                 if (ms < best) { best = ms; cfg = c; }
             }
             cudaEventDestroy(e0); cudaEventDestroy(e1);
-            if (getenv("SN_TC_VERBOSE")) fprintf(stderr, "[surfacenet_b200] tuned %s S=%d P=%d n=%d: AD=%d NB=%d (%.3f ms)\n", kUnits[u].name, S, P, n_pc, cfg.AD, cfg.NB, best / 2);
+            if (getenv("SN_TC_VERBOSE")) fprintf(stderr, "[surfacenet_b200] tuned %s S=%d P=%d n=%d: AD=%d NB=%d persist=%d (%.3f ms)\n", kUnits[u].name, S, P, n_pc, cfg.AD, cfg.NB, cfg.persist, best / 2);
         }
         st->tuned[key] = std::make_pair(cfg, work);
         tune_file_save(st);
@@ -790,9 +859,13 @@ static int pool_launch(const __half* in, int n, int Cpad, int P, int S, __half* 
 }
 static int upsample_blk_launch(const __half* in, const float* W, int k, int f, int n, int Cpad, int P, int S, __half* out, int cg_total,
                                int cg_off, cudaStream_t st) {
-    const long long total = (long long)n * (Cpad / 8) * S * f * S * f * S * f;
-    if (!total) return SN_OK;
-    upsample_blk_kernel<<<ew_blocks(total), 256, 0, st>>>(in, W, k, f, Cpad / 8, P, S, total, out, cg_total, cg_off);
+    const int So = S * f, cg_in = Cpad / 8;
+    if (!n || !S) return SN_OK;
+    SN_CHECK_ARG((k == 3 && f == 2) || (k == 5 && f == 4), "upsample: only (k=3, x2) and (k=5, x4) exist in SurfaceNet (nets/layers.py:383)");
+    SN_CHECK_ARG(So <= 65535 && (long long)n * cg_in <= 65535, "upsample: grid too large");
+    dim3 grid((unsigned)cdiv((long long)So * So, 256), (unsigned)So, (unsigned)(n * cg_in));
+    if (f == 2) upsample_blk_kernel<2, 3><<<grid, 256, 0, st>>>(in, W, cg_in, P, S, out, cg_total, cg_off);
+    else upsample_blk_kernel<4, 5><<<grid, 256, 0, st>>>(in, W, cg_in, P, S, out, cg_total, cg_off);
     SN_LAUNCHED();
     return SN_OK;
 }

@@ -135,6 +135,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its children; the CPU arm is meant to use every host core
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = str(os.cpu_count() or 1)
     import numpy as np  # noqa: F401
     from surfacenet_b200 import weights
     from tests import util

@@ -282,6 +282,20 @@ def test_forward_single_pair_and_odd_batch(torch_cuda, params, cams, mode):
     assert np.abs(fused - o).max() <= PROB_TOL
 
 
+def test_forward_s64_full_size_exact(torch_cuda, params, cams):
+    """BASELINE full cube size (64^3), 1 cube x 2 pairs, tensor-core exact mode vs the torch-CPU fp32 oracle."""
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet
+    X, *_ = _real_like_X(cams, 64, n_cubes=1, n_vp=2, seed=11)
+    w = np.array([[0.35, 0.8]], np.float32)
+    fused_o, unf_o = so.nViewPair_SurfaceNet_fn(X, params, w, N_vp=2, chunk=1)
+    _, fn = SurfaceNet.SurfaceNet_inference(2, params, mode="exact")
+    fused, unf = fn(X, w)
+    e_f, e_u = np.abs(fused - fused_o).max(), np.abs(unf - unf_o).max()
+    print("s=64 exact: max-abs fused %.3g unfused %.3g" % (e_f, e_u))
+    assert e_f <= PROB_TOL and e_u <= PROB_TOL
+
+
 def test_forward_fast_mode_reports_error(torch_cuda, params, cams):
     """Single-pass fp16 operands: explicitly NOT a parity mode; its error is measured and bounded loosely."""
     from oracle import surfacenet_oracle as so

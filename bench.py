@@ -253,6 +253,13 @@ def run_gpu(args, wl):
     _lib.lib.sn_profile_enable(0)
     clocks = sampler.window(*win) if sampler else None
     ms_e2e, _, _ = timed(step_host, args.steps, max(args.warmup, 1))
+    h2d_e2e, d2h_e2e = hp.h2d_bytes, hp.d2h_bytes
+    # the same loop body including colour fusion + dense2sparse (main_reconstruct.py:150-162): only kept voxels cross PCIe
+    Dc = {32: 26, 64: 52}.get(D, D)                                          # params.py:107 __cube_Dcenter
+    def step_sparse():
+        return hp.infer_batch_sparse(pairs, xyz, resol, w, D, Dc)
+    ms_sparse, _, _ = timed(step_sparse, max(2, args.steps // 2), 1)
+    d2h_sparse = hp.d2h_bytes
     if sampler:
         sampler.stop()
 
@@ -292,8 +299,10 @@ def run_gpu(args, wl):
                        "parallelism": "cube-sharded x%d, one all-gather of prob+votes per step" % world},
             "pair_voxels_per_s": world * pair_vox_step / (ms_dev * 1e-3),
             "path_tflops": FLOP_PER_PAIR_VOXEL * world * pair_vox_step / (ms_dev * 1e-3) / 1e12,
-            "e2e": {"value": fused_vox / (ms_e2e * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
+            "e2e": {"value": fused_vox / (ms_e2e * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d_e2e, "d2h_bytes_per_step": d2h_e2e,
                     "ms_per_step": ms_e2e},
+            "e2e_sparse": {"value": fused_vox / (ms_sparse * 1e-3), "unit": "voxels/s", "ms_per_step": ms_sparse, "d2h_bytes_per_step": d2h_sparse,
+                           "what": "numpy in -> per-cube sparse lists out (adds colour fusion + centre-crop/threshold compaction on the GPU; no all-gather)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel, merge_conv2 launch (3x3x3 100->100 + fused merge_conv3/sigmoid), %d launches/step" % (cnt_u[dom] // args.steps),

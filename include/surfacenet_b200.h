@@ -170,6 +170,42 @@ int sn_infer_batch_host(const sn_net* net, const uint8_t* images_dev, const int6
                         float* fused_out_host, void* pred16_out_host, uint8_t* votes_out_host,
                         void* workspace_dev, int64_t workspace_bytes, int mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" rows of the scope table: the immediate consumers of the dense outputs.
+ *
+ * utils/utils.py:8-42  generate_voxelLevelWeighted_coloredCubes(viewPair_coloredCubes, viewPair_surf_predictions, weight4viewPair)
+ *   cvc_dev      (n_cubes*n_vp, 6, vol) f32 colours; mean6_dev != NULL adds the mean back first, in fp32, exactly as
+ *                main_reconstruct.py:150 does to the mean-subtracted tensor
+ *   unfused_dev  (n_cubes, n_vp, vol) f32;  w_dev (n_cubes, n_vp) f32 (may be NULL when n_vp == 1)
+ *   rgb_out_dev  (n_cubes, 3, vol) u8  -- bit-exact: every fp32 operation is rounded individually in numpy's order
+ */
+int sn_color_fusion(const float* cvc_dev, const float* mean6_dev, const float* unfused_dev, const float* w_dev, int n_cubes,
+                    int n_vp, int64_t vol, uint8_t* rgb_out_dev, void* stream);
+
+/* utils/sparseCubes.py:9-77  dense2sparse(..., enable_centerCrop=True, cube_Dcenter, enable_rayPooling) on device-resident
+ * dense volumes: centre crop [(D-Dc)/2, (D-Dc)/2+Dc)^3, keep `pred > min_prob` (rayPool_thresh == 0, the hot-loop call
+ * site main_reconstruct.py:156) or `votes >= rayPool_thresh` (> 0), ordered compaction in np.where order.
+ *   pred16_dev (n_cubes,D,D,D) f16; rgb_dev (n_cubes,3,D,D,D) u8 or NULL; votes_dev (n_cubes,D,D,D) u8 or NULL
+ *   cube_count_dev (n_cubes) i32 kept voxels per cube; cube_offset_dev (n_cubes+1) i32 start of each cube in the flat
+ *   outputs, last entry = total;  ijk_out (cap,3) u8 crop coordinates, pred_out (cap) f16, rgb_out (cap,3) u8, votes_out (cap) u8
+ *   capacity = entries the flat outputs can hold (n_cubes*Dc^3 always suffices); extra voxels are dropped, the counts stay exact.
+ */
+int64_t sn_dense2sparse_workspace_bytes(int n_cubes, int D, int Dcenter);
+int sn_dense2sparse(const void* pred16_dev, const uint8_t* rgb_dev, const uint8_t* votes_dev, int n_cubes, int D, int Dcenter,
+                    float min_prob_f16, int rayPool_thresh, int32_t* cube_count_dev, int32_t* cube_offset_dev,
+                    uint8_t* ijk_out_dev, void* pred_out_dev, uint8_t* rgb_out_dev, uint8_t* votes_out_dev, int64_t capacity,
+                    void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* main_reconstruct.py:134-162 including the colour fusion (150-152) and the sparsification (154-162): like sn_infer_batch,
+ * but the results leave the device as the compacted per-cube lists sparseCubes.append_dense_2sparseList builds. */
+int64_t sn_infer_batch_sparse_workspace_bytes(const sn_net* net, int n_cubes, int n_vp, int D, int Dcenter, int mode);
+int sn_infer_batch_sparse(const sn_net* net, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
+                          int n_views, const double* P_dev, const float* xyz_dev, const float* resol_dev,
+                          const int32_t* viewpairs_dev, const float* w_dev, int n_cubes, int n_vp, int D, int Dcenter,
+                          float min_prob_f16, int rayPool_thresh, int32_t* cube_count_dev, int32_t* cube_offset_dev,
+                          uint8_t* ijk_out_dev, void* pred_out_dev, uint8_t* rgb_out_dev, uint8_t* votes_out_dev, int64_t capacity,
+                          void* workspace_dev, int64_t workspace_bytes, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

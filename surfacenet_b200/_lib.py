@@ -46,6 +46,11 @@ SIGNATURES = {
     "sn_infer_batch_workspace_bytes": (_i64, [_p, _i, _i, _i, _i]),
     "sn_infer_batch": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p, _i64, _i, _p]),
     "sn_infer_batch_host": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _i64, _i, _p]),
+    "sn_color_fusion": (_i, [_p, _p, _p, _p, _i, _i, _i64, _p, _p]),
+    "sn_dense2sparse_workspace_bytes": (_i64, [_i, _i, _i]),
+    "sn_dense2sparse": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _p]),
+    "sn_infer_batch_sparse_workspace_bytes": (_i64, [_p, _i, _i, _i, _i, _i]),
+    "sn_infer_batch_sparse": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i, _p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)          # AttributeError here = the library does not export a declared symbol

@@ -113,3 +113,56 @@ extern "C" int sn_infer_batch_host(const sn_net* h, const uint8_t* images_dev, c
     SN_CUDA(cudaStreamSynchronize(st));
     return SN_OK;
 }
+
+// ---- main_reconstruct.py:134-162 with colour fusion and sparsification ------------------------------------------------
+static int64_t sparse_ws_layout(const sn_net* h, int n_cubes, int n_vp, int D, int Dc, int mode, int64_t off[6]) {
+    const int64_t V = (int64_t)D * D * D;
+    const int64_t inner = sn_infer_batch_workspace_bytes(h, n_cubes, n_vp, D, mode);
+    const int64_t d2s = sn_dense2sparse_workspace_bytes(n_cubes, D, Dc);
+    if (inner < 0 || d2s < 0) return -1;
+    int64_t o = align_up(inner, 256);
+    off[0] = o; o += align_up((int64_t)n_cubes * n_vp * V * 4, 256);     // unfused
+    off[1] = o; o += align_up(n_cubes * V * 4, 256);                    // fused
+    off[2] = o; o += align_up(n_cubes * V * 2, 256);                    // pred16
+    off[3] = o; o += align_up(n_cubes * V, 256);                        // votes
+    off[4] = o; o += align_up(n_cubes * V * 3, 256);                    // rgb
+    off[5] = o; o += align_up(d2s, 256);
+    return o;
+}
+
+extern "C" int64_t sn_infer_batch_sparse_workspace_bytes(const sn_net* h, int n_cubes, int n_vp, int D, int Dcenter, int mode) {
+    if (!h || n_cubes < 0 || n_vp < 1) return -1;
+    int64_t off[6];
+    return sparse_ws_layout(h, n_cubes, n_vp, D, Dcenter, mode, off);
+}
+
+extern "C" int sn_infer_batch_sparse(const sn_net* h, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
+                                     int n_views, const double* P_dev, const float* xyz_dev, const float* resol_dev,
+                                     const int32_t* viewpairs_dev, const float* w_dev, int n_cubes, int n_vp, int D, int Dcenter,
+                                     float min_prob_f16, int rayPool_thresh, int32_t* cube_count_dev, int32_t* cube_offset_dev,
+                                     uint8_t* ijk_out_dev, void* pred_out_dev, uint8_t* rgb_out_dev, uint8_t* votes_out_dev, int64_t capacity,
+                                     void* workspace_dev, int64_t workspace_bytes, int mode, void* stream) {
+    SN_CHECK_ARG(h && n_cubes >= 0 && n_vp >= 1, "sn_infer_batch_sparse: bad arguments");
+    if (n_cubes == 0) return SN_OK;
+    int64_t off[6];
+    const int64_t need = sparse_ws_layout(h, n_cubes, n_vp, D, Dcenter, mode, off);
+    if (need < 0) return SN_ERR_INVALID;
+    if (!workspace_dev || workspace_bytes < need) { set_error("sn_infer_batch_sparse: workspace %lld B < %lld B", (long long)workspace_bytes, (long long)need); return SN_ERR_NOMEM; }
+    char* ws = (char*)workspace_dev;
+    float* unf = (float*)(ws + off[0]); float* fused = (float*)(ws + off[1]);
+    void* p16 = ws + off[2]; uint8_t* votes = (uint8_t*)(ws + off[3]); uint8_t* rgb = (uint8_t*)(ws + off[4]);
+    const int64_t V = (int64_t)D * D * D;
+    int32_t* flags = nullptr;
+    int rc = infer_enqueue(h, images_dev, img_offset_dev, img_hw_dev, n_views, P_dev, xyz_dev, resol_dev, viewpairs_dev, w_dev, n_cubes, n_vp, D,
+                           min_prob_f16, fused, n_vp > 1 ? unf : nullptr, p16, votes, workspace_dev, off[0], mode, stream, &flags);
+    if (rc != SN_OK) return rc;
+    // main_reconstruct.py:150-152: colours = mean-subtracted CVC (head of the workspace) + mean, fused with w * unfused p
+    const float* X = (const float*)workspace_dev;
+    rc = sn_color_fusion(X, h->net.mean6, n_vp > 1 ? unf : fused, w_dev, n_cubes, n_vp, V, rgb, stream);
+    if (rc != SN_OK) return rc;
+    // main_reconstruct.py:154-162 -> sparseCubes.dense2sparse
+    rc = sn_dense2sparse(p16, rgb, votes, n_cubes, D, Dcenter, min_prob_f16, rayPool_thresh, cube_count_dev, cube_offset_dev, ijk_out_dev,
+                         pred_out_dev, rgb_out_dev, votes_out_dev, capacity, ws + off[5], workspace_bytes - off[5], stream);
+    if (rc != SN_OK) return rc;
+    return flags ? raypool_check(flags, stream) : SN_OK;
+}

@@ -542,7 +542,7 @@ static inline int ew_blocks(long long total) { return (int)std::min<long long>(c
 
 // ------------------------------------------------------------------------------------------------
 // host side: weight preparation, tensor maps, launches
-struct TileCfg { int AD, NB, persist; };          // d-planes per CTA, weight-ring depth, persistent CTAs (1) or one CTA per tile (0)
+struct TileCfg { int AD, NB, persist; };          // d-planes per CTA, weight-ring depth, CTA scheduling (see conv_tc_launch_cfg)
 struct TcVariant {                                 // [0] exact (P = 2), [1] fast (P = 1): own N tiling and weight image
     int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0};
     long long nt_woff[TC_MAX_NT] = {0, 0, 0, 0};
@@ -706,7 +706,7 @@ static std::vector<TileCfg> tile_candidates(const ConvUnit& cu, int Nmax, int S,
         if ((double)S / (double)(cdiv(S, ad) * ad) < 0.85 && ad > 1) continue;       // too many planes outside the volume
         for (int nb : {3, 6}) {
             if (env_nb && nb != env_nb) continue;
-            if (tc_smem_bytes(cu, Nmax, P, {ad, nb, 0}) <= 227 * 1024) { out.push_back({ad, nb, 0}); out.push_back({ad, nb, 1}); }
+            if (tc_smem_bytes(cu, Nmax, P, {ad, nb, 0}) <= 227 * 1024) { out.push_back({ad, nb, 0}); out.push_back({ad, nb, 1}); out.push_back({ad, nb, 2}); }
         }
     }
     if (out.empty()) out.push_back({1, 2, 1});
@@ -760,7 +760,9 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
 
     const size_t smem = tc_smem_bytes(cu, Nmax, P, cfg);
     p.n_tiles = (long long)a.n_pc * p.tiles_d * p.tiles_h * p.tiles_w * tv.n_ntiles;
-    p.nbuf = (cfg.persist && 2 * AD * P * Nmax <= 512) ? 2 : 1;
+    // persist: 0 = one CTA per tile, 1 = persistent with two TMEM accumulator sets when they fit, 2 = persistent with one
+    // set (half the TMEM columns, so twice as many CTAs can share an SM)
+    p.nbuf = (cfg.persist == 1 && 2 * AD * P * Nmax <= 512) ? 2 : 1;
     SN_CHECK_ARG(smem <= 227 * 1024 && AD * P * Nmax <= 512 && Nmax == tv.nt_size[0], "conv_tc: bad tile configuration (smem=%zu)", smem);
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; SN_CUDA(cudaGetDevice(&dev)); SN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }

@@ -118,6 +118,40 @@ class HotPath:
                     votes=None if h_votes is None else h_votes.numpy())
 
 
+    # ---- fused call with colour fusion + sparsification (main_reconstruct.py:134-162 in full) ---------
+    def infer_batch_sparse(self, viewPairs, xyz, resol, w, D, cube_Dcenter, rayPool_thresh=0):
+        """numpy arguments as infer_batch_host.  Everything up to sparseCubes.dense2sparse stays on the GPU; only the kept
+        voxels cross PCIe.  -> dict(counts (B,), offsets (B+1,), ijk u8 (T,3) crop coordinates, pred f16 (T,), rgb u8 (T,3),
+        votes u8 (T,)), ordered per cube exactly like the lists append_dense_2sparseList builds."""
+        t = self.torch
+        pairs = np.asarray(viewPairs)
+        B, n_vp = self._check_batch(pairs, np.asarray(xyz), np.asarray(resol), None if w is None else np.asarray(w))
+        self.scene.check_views(pairs)
+        D, Dc = int(D), int(cube_Dcenter)
+        if B == 0:
+            return dict(counts=np.zeros(0, np.int32), offsets=np.zeros(1, np.int32), ijk=np.zeros((0, 3), np.uint8),
+                        pred=np.zeros(0, np.float16), rgb=np.zeros((0, 3), np.uint8), votes=np.zeros(0, np.uint8))
+        dev = lambda a, dt: t.from_numpy(np.ascontiguousarray(a, dtype=dt)).cuda()
+        d_pairs, d_xyz, d_resol = dev(pairs, np.int32), dev(xyz, np.float32), dev(resol, np.float32)
+        d_w = dev(w, np.float32) if n_vp > 1 else None
+        cap = B * Dc ** 3
+        counts = t.zeros(B, dtype=t.int32, device="cuda"); offsets = t.zeros(B + 1, dtype=t.int32, device="cuda")
+        ijk = t.empty((cap, 3), dtype=t.uint8, device="cuda"); pred = t.empty(cap, dtype=t.float16, device="cuda")
+        rgb = t.empty((cap, 3), dtype=t.uint8, device="cuda"); votes = t.empty(cap, dtype=t.uint8, device="cuda")
+        ws = self._workspace(_lib.lib.sn_infer_batch_sparse_workspace_bytes(self.net.handle, B, n_vp, D, Dc, self.mode))
+        sc = self.scene
+        _lib.check(_lib.lib.sn_infer_batch_sparse(
+            self.net.handle, _lib.ptr(sc.images), _lib.ptr(sc.img_offset), _lib.ptr(sc.img_hw), sc.n_views, _lib.ptr(sc.P),
+            _lib.ptr(d_xyz), _lib.ptr(d_resol), _lib.ptr(d_pairs), _lib.ptr(d_w), B, n_vp, D, Dc, self._min_prob_f16(), int(rayPool_thresh),
+            _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(ijk), _lib.ptr(pred), _lib.ptr(rgb), _lib.ptr(votes), cap,
+            _lib.ptr(ws), ws.numel(), self.mode, _lib.stream_ptr()))
+        off = offsets.cpu().numpy()
+        T = int(off[-1])
+        self.d2h_bytes = (B * 2 + 1) * 4 + T * 8
+        return dict(counts=counts.cpu().numpy(), offsets=off, ijk=ijk[:T].cpu().numpy(), pred=pred[:T].cpu().numpy(),
+                    rgb=rgb[:T].cpu().numpy(), votes=votes[:T].cpu().numpy())
+
+
 # ---- cube sharding (SURVEY.md 8(e)) ---------------------------------------------------------------
 def shard_bounds(n_cubes, world_size):
     """Contiguous, equal-count split of the cube axis: every rank gets ceil(n/world) slots (the last

@@ -79,6 +79,21 @@ def load_ref_colorfusion():
     return ref_utils.generate_voxelLevelWeighted_coloredCubes
 
 
+def load_ref_sparse(rp_module):
+    """utils/sparseCubes.py imports cPickle / plyfile at module level; dense2sparse and append_dense_2sparseList are
+    extracted as text and executed alone.  Mechanical fix: the py2 integer divisions `(D_orig-cube_Dcenter)/2`
+    (sparseCubes.py:51) become `//` (SURVEY.md F13)."""
+    src = open(os.path.join(REF, "utils", "sparseCubes.py")).read()
+    a = src.index("def dense2sparse(")
+    b = src.index("\ndef ", src.index("def append_dense_2sparseList(") + 10)
+    body = src[a:b]
+    assert body.count("(D_orig-cube_Dcenter)/2") == 2
+    body = body.replace("(D_orig-cube_Dcenter)/2", "(D_orig-cube_Dcenter)//2")
+    ns = {"np": np, "rayPooling": rp_module}
+    exec(compile(body, os.path.join(REF, "utils", "sparseCubes.py"), "exec"), ns)
+    return ns["dense2sparse"], ns["append_dense_2sparseList"]
+
+
 def dtu_cameras():
     cams = np.empty((49, 3, 4), dtype=np.float64)
     for v in range(1, 50):
@@ -142,6 +157,25 @@ def main():
     cc = rs.randint(0, 256, size=(2 * 3, 6, 8, 8, 8)).astype(np.float32)
     pr = rs.rand(2, 3, 8, 8, 8).astype(np.float32); ww = (rs.rand(2, 3) + 0.1).astype(np.float32)
     out["cf_cc"], out["cf_pred"], out["cf_w"], out["cf_out"] = cc.astype(np.uint8), pr, ww, fuse(cc, pr, ww)
+
+    # ---- 6. sparseCubes.dense2sparse / append_dense_2sparseList ("next" row N1) -------------------
+    d2s, append = load_ref_sparse(RP)
+    for name, case in util.sparse_cases(cams).items():
+        res = append(prediction_sub=case["pred"], rgb_sub=case["rgb"], param_sub=case["param"], viewPair_sub=case["pairs"],
+                     min_prob=case["min_prob"], rayPool_thresh=0, enable_centerCrop=True, cube_Dcenter=case["Dcenter"],
+                     enable_rayPooling=True, cameraPOs=cams, cameraTs=np.zeros((cams.shape[0], 3)),
+                     prediction_list=[], rgb_list=[], vxl_ijk_list=[], rayPooling_votes_list=[], cube_ijk_np=None, param_np=None, viewPair_np=None)
+        pl, rl, il, vl, cube_ijk, param_np, vp_np = res
+        out["sp_" + name + "_counts"] = np.array([len(x) for x in pl], np.int64)
+        out["sp_" + name + "_pred"] = np.concatenate(pl) if pl else np.zeros(0, np.float16)
+        out["sp_" + name + "_rgb"] = np.concatenate(rl) if rl else np.zeros((0, 3), np.uint8)
+        out["sp_" + name + "_ijk"] = np.concatenate(il) if il else np.zeros((0, 3), np.uint8)
+        out["sp_" + name + "_votes"] = np.concatenate(vl) if vl else np.zeros(0, np.uint8)
+        out["sp_" + name + "_cube_ijk"] = np.asarray(cube_ijk)
+        out["sp_" + name + "_xyz"] = np.asarray(param_np["xyz"]); out["sp_" + name + "_resol"] = np.asarray(param_np["resol"])
+        out["sp_" + name + "_viewPair"] = np.asarray(vp_np)
+        assert not pl or (pl[0].dtype == np.float16 and il[0].dtype == np.uint8 and vl[0].dtype == np.uint8)
+        print("sparse", name, "kept voxels per non-empty cube", out["sp_" + name + "_counts"])
 
     np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_golden.npz"), {k: v.shape for k, v in out.items()})

@@ -380,3 +380,81 @@ def test_infer_batch_device_equals_host_entry(torch_cuda, params, cams):
     assert d["unfused"].shape == (3, 2, D, D, D)
     empty = hp.infer_batch_host(pairs[:0], xyz[:0], resol[:0], w[:0], D)
     assert empty["fused"].shape == (0, 1, D, D, D)
+
+
+# ---- "next" rows N1 / N2: colour fusion and dense -> sparse ------------------------------------------------
+def test_color_fusion_matches_reference_outputs(torch_cuda, golden):
+    from surfacenet_b200 import utils as sn_utils
+    out = sn_utils.generate_voxelLevelWeighted_coloredCubes(golden["cf_cc"].astype(np.float32), golden["cf_pred"], golden["cf_w"])
+    assert out.dtype == np.uint8 and np.array_equal(out, golden["cf_out"])          # bit-exact
+
+
+def test_color_fusion_s32_vs_oracle(torch_cuda):
+    from oracle import sparse_oracle
+    from surfacenet_b200 import utils as sn_utils
+    rs = np.random.RandomState(5)
+    cc = rs.randint(0, 256, size=(3 * 5, 6, 32, 32, 32)).astype(np.float32)
+    cc = (cc - util.MEAN6[None, :, None, None, None]) + util.MEAN6[None, :, None, None, None]     # main_reconstruct.py:143,150 round trip
+    p = rs.rand(3, 5, 32, 32, 32).astype(np.float32) * 0.98 + 0.01
+    w = (rs.rand(3, 5) + 0.1).astype(np.float32)
+    assert np.array_equal(sn_utils.generate_voxelLevelWeighted_coloredCubes(cc, p, w),
+                          sparse_oracle.generate_voxelLevelWeighted_coloredCubes(cc, p, w))
+    with pytest.raises(ValueError):
+        sn_utils.generate_voxelLevelWeighted_coloredCubes(cc, p, w[:, :3])
+
+
+@pytest.mark.parametrize("name", ["d16", "d32", "all_empty"])
+def test_dense2sparse_matches_reference_outputs(torch_cuda, golden, cams, name):
+    from surfacenet_b200 import sparseCubes
+    from tests.test_oracle_golden import _check_sparse
+    case = util.sparse_cases(cams)[name]
+    res = sparseCubes.append_dense_2sparseList(case["pred"], case["rgb"], case["param"], case["pairs"], min_prob=case["min_prob"],
+                                               rayPool_thresh=0, enable_centerCrop=True, cube_Dcenter=case["Dcenter"],
+                                               enable_rayPooling=True, cameraPOs=cams, cameraTs=None,
+                                               prediction_list=[], rgb_list=[], vxl_ijk_list=[], rayPooling_votes_list=[])
+    _check_sparse(res, golden, name)
+
+
+def test_dense2sparse_s64_raypool_threshold_vs_oracle(torch_cuda, cams):
+    """Full cube size (64^3, centre 52^3: params.py:107) and the votes >= rayPool_thresh branch (sparseCubes.py:64)."""
+    from oracle import sparse_oracle
+    from surfacenet_b200 import sparseCubes
+    rs = np.random.RandomState(8)
+    n, D, Dc = 2, 64, 52
+    pred = np.stack([util.sheet_prediction(D, 0.4 * i, 0.07) for i in range(n)])
+    rgb = rs.randint(0, 256, size=(n, D, D, D, 3)).astype(np.uint8)
+    param = np.zeros(n, util.PARAM_DTYPE)
+    param["xyz"] = np.array([[20.0, -12.5, 630.0], [-10.3, 30.7, 655.1]], np.float32); param["resol"] = np.float32(0.4)
+    pairs = np.array([[[0, 5], [17, 22], [5, 30]], [[1, 2], [3, 4], [5, 6]]], np.uint16)
+    for thresh in (0, 2):
+        a = sparseCubes.dense2sparse(pred, rgb, param, pairs, 0.46, thresh, True, Dc, True, cams, None)
+        b = sparse_oracle.dense2sparse(pred, rgb, param, pairs, 0.46, thresh, True, Dc, True, cams, None)
+        assert a[0] == b[0] and len(a[0]) == n
+        for k in (1, 2, 3, 4):
+            assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a[k], b[k])), "list %d differs (thresh %d)" % (k, thresh)
+        assert np.array_equal(a[5]["xyz"], b[5]["xyz"])
+
+
+def test_infer_batch_sparse_matches_dense_pipeline(torch_cuda, params, cams):
+    """The fully fused call (CVC -> net -> fusion -> colours -> votes -> compaction) against the reference sequence of
+    main_reconstruct.py:143-162 applied to the device's own dense outputs."""
+    import torch
+    from oracle import cvc_oracle, sparse_oracle
+    from surfacenet_b200 import SurfaceNet, pipeline
+    from surfacenet_b200.device import DeviceScene
+    D, Dc = 32, 26
+    X, pairs, xyz, resol, imgs = _real_like_X(cams, D, n_cubes=2, n_vp=3, seed=9)
+    w = (np.random.RandomState(6).rand(2, 3) + 0.1).astype(np.float32)
+    hp = pipeline.HotPath(SurfaceNet.Net(params), DeviceScene(cams, imgs), mode="exact")
+    sp = hp.infer_batch_sparse(pairs, xyz, resol, w, D, Dc)
+    dense = hp.infer_batch(torch.from_numpy(pairs.astype(np.int32)).cuda(), torch.from_numpy(xyz).cuda(), torch.from_numpy(resol).cuda(),
+                           torch.from_numpy(w).cuda(), D, want_unfused=True)
+    Xc = X + util.MEAN6[None, :, None, None, None]                                              # main_reconstruct.py:150
+    rgb = sparse_oracle.generate_voxelLevelWeighted_coloredCubes(Xc, dense["unfused"].cpu().numpy(), w)
+    param = np.zeros(2, util.PARAM_DTYPE); param["xyz"] = xyz; param["resol"] = resol
+    ref = sparse_oracle.append_dense_2sparseList(dense["fused"].cpu().numpy(), rgb, param, pairs, min_prob=0.46, rayPool_thresh=0,
+                                                 enable_centerCrop=True, cube_Dcenter=Dc, enable_rayPooling=True, cameraPOs=cams, cameraTs=None)
+    pl, rl, il, vl = ref[:4]
+    assert sp["counts"].sum() == sum(len(x) for x in pl) > 0
+    assert np.array_equal(sp["pred"], np.concatenate(pl)) and np.array_equal(sp["ijk"], np.concatenate(il))
+    assert np.array_equal(sp["rgb"], np.concatenate(rl)) and np.array_equal(sp["votes"], np.concatenate(vl))

@@ -2,7 +2,7 @@
 (b) golden outputs produced by executing the reference code (tests/golden/make_golden.py)."""
 import numpy as np
 import pytest
-from oracle import camera_oracle, cvc_oracle, raypool_oracle, surfacenet_oracle
+from oracle import camera_oracle, cvc_oracle, raypool_oracle, sparse_oracle, surfacenet_oracle
 from tests import util
 
 
@@ -86,3 +86,31 @@ def test_upsample_micro_cases():
     assert np.allclose(y4, [1, 2 / 3, 1.0, 4 / 3, 2, 4 / 3, 2 / 3, 0], atol=1e-6)
     y2 = surfacenet_oracle.upsample(x, surfacenet_oracle.W_5D(3), 2)[0, 0, :, 0, 0].numpy()
     assert np.allclose(y2, [1, 1.5, 2, 1.0], atol=1e-6)
+
+
+def test_colorfusion_oracle_matches_reference_outputs(golden):
+    out = sparse_oracle.generate_voxelLevelWeighted_coloredCubes(golden["cf_cc"].astype(np.float32), golden["cf_pred"], golden["cf_w"])
+    assert out.dtype == np.uint8 and np.array_equal(out, golden["cf_out"])
+
+
+def _check_sparse(res, golden, name):
+    pl, rl, il, vl, cube_ijk, param_np, vp_np = res
+    assert np.array_equal(np.array([len(x) for x in pl], np.int64), golden["sp_" + name + "_counts"])
+    cat = lambda l, shape, dt: np.concatenate(l) if l else np.zeros(shape, dt)
+    assert np.array_equal(cat(pl, 0, np.float16), golden["sp_" + name + "_pred"])
+    assert np.array_equal(cat(rl, (0, 3), np.uint8), golden["sp_" + name + "_rgb"])
+    assert np.array_equal(cat(il, (0, 3), np.uint8), golden["sp_" + name + "_ijk"])
+    assert np.array_equal(cat(vl, 0, np.uint8), golden["sp_" + name + "_votes"])
+    assert np.array_equal(np.asarray(cube_ijk), golden["sp_" + name + "_cube_ijk"])
+    assert np.array_equal(np.asarray(param_np["xyz"]), golden["sp_" + name + "_xyz"])
+    assert np.array_equal(np.asarray(vp_np), golden["sp_" + name + "_viewPair"])
+    assert all(a.dtype == np.float16 for a in pl) and all(a.dtype == np.uint8 for a in il + rl + vl)
+
+
+@pytest.mark.parametrize("name", ["d16", "d32", "all_empty"])
+def test_dense2sparse_oracle_matches_reference_outputs(golden, cams, name):
+    case = util.sparse_cases(cams)[name]
+    res = sparse_oracle.append_dense_2sparseList(case["pred"], case["rgb"], case["param"], case["pairs"], min_prob=case["min_prob"],
+                                                 rayPool_thresh=0, enable_centerCrop=True, cube_Dcenter=case["Dcenter"],
+                                                 enable_rayPooling=True, cameraPOs=cams, cameraTs=None)
+    _check_sparse(res, golden, name)

@@ -85,3 +85,27 @@ def raypool_cases(cams):
     c["exact_thresh"] = dict(cameraPOs=cams, pred=np.where(rs.rand(8, 8, 8) < 0.5, np.float16(0.46), np.float16(0.4602)).astype(np.float16),
                              pairs=np.array([[20, 21]]), xyz=xyz, resol=f32(0.4), thresh=0.46)
     return c
+
+
+PARAM_DTYPE = np.dtype([("xyz", np.float32, (3,)), ("ijk", np.uint32, (3,)), ("resol", np.float32)])   # utils/scene.py:55
+
+
+def sparse_cases(cams):
+    """Dense batches as main_reconstruct.py:154-162 hands them to sparseCubes.append_dense_2sparseList."""
+    c = {}
+    rs = np.random.RandomState(21)
+    def batch(D, n, n_vp, empty=()):
+        pred = np.stack([sheet_prediction(D, 0.7 * i, 0.12).astype(np.float32) for i in range(n)])[:, None]     # (N,1,D,D,D) f32
+        for e in empty:
+            pred[e] = 0.2
+        rgb = rs.randint(0, 256, size=(n, 3, D, D, D)).astype(np.uint8)
+        param = np.zeros(n, PARAM_DTYPE)
+        param["xyz"] = (np.array([10.0, -30.0, 620.0]) + rs.rand(n, 3) * 30).astype(np.float32)
+        param["ijk"] = rs.randint(0, 40, size=(n, 3))
+        param["resol"] = np.float32(0.4)
+        pairs = rs.randint(0, 49, size=(n, n_vp, 2))
+        return dict(pred=pred, rgb=rgb, param=param, pairs=pairs, min_prob=0.46)
+    c["d16"] = dict(batch(16, 3, 2, empty=(1,)), Dcenter=12)
+    c["d32"] = dict(batch(32, 2, 3), Dcenter=26)                   # params.py:107 __cube_Dcenter[32] = 26
+    c["all_empty"] = dict(batch(8, 2, 1, empty=(0, 1)), Dcenter=6)
+    return c

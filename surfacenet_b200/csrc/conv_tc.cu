@@ -107,7 +107,7 @@ constexpr int EPI_BLK = 0, EPI_FINAL = 1;
 constexpr int TC_MAX_NT = 4;
 
 struct ConvTcParams {
-    int S, n_pc, dil, K, taps, n_cblk, cg_in, NB, nbuf;
+    int S, n_pc, dil, K, taps, n_cblk, cg_in, NB, nbuf, TPS;   // TPS = taps per weight-ring slot: 1, K (the kw taps of one (kd,kh)) or K*K
     long long n_tiles;              // tiles_w * tiles_h * tiles_d * n_pc * n_ntiles
     int PW, HH, HD;                 // halo tile extents (voxels)
     int a_prec_bytes;               // bytes of one precision plane of one A stage = PW*HH*HD*32
@@ -181,7 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
     const int NB = p.NB;
     const int Nmax = p.nt_size[0];                                    // N tiles are sorted largest first
     const uint32_t a_stage_bytes = (uint32_t)p.a_prec_bytes * P;
-    const uint32_t b_slot_bytes = (uint32_t)Nmax * 32 * P;            // ring slot, sized for the largest N tile
+    const uint32_t b_slot_bytes = (uint32_t)Nmax * 32 * P * p.TPS;    // ring slot: TPS taps of the largest N tile
     unsigned char* smA = smem;                                        // [2][P][2 groups][HD][HH][PW][8] fp16
     unsigned char* smB = smem + 2 * a_stage_bytes;                    // [NB][2][P][N/8][8][8] fp16
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)NB * b_slot_bytes);
@@ -233,11 +233,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
         }
     } else if (warp == 1) {
         // ===== B producer: the (channel block, tap) weight tile, already in canonical layout in HBM =====
-        const int total = p.n_cblk * p.taps;
+        const int total = p.n_cblk * p.taps / p.TPS;
         int s = 0; uint32_t ph = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const TileCoord c = tile_coord<AD>(p, t);
-            const uint32_t stage_bytes = (uint32_t)p.nt_size[c.nt] * 32 * P;
+            const uint32_t stage_bytes = (uint32_t)p.nt_size[c.nt] * 32 * P * p.TPS;
             const unsigned char* wsrc = p.weights + p.nt_woff[c.nt];
             for (int it = 0; it < total; ++it) {
                 mbar_wait(&b_empty[s], ph ^ 1);
@@ -271,6 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)((P * N) >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, M=128
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t b_lbo = (uint32_t)(P * N) << 16;                  // one K half of the stage: P*N rows of 16 B
+            const uint32_t tapB16 = (uint32_t)(2 * P * N);                   // one tap of the slot = 2 K halves
             const uint32_t buf = (nbuf == 2) ? (j & 1) : 0;
             const uint32_t use = (nbuf == 2) ? (j >> 1) : j;                 // how often this accumulator set was used before
             const uint32_t dbase = tmem_base + buf * buf_cols;
@@ -283,33 +284,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                 tc_fence_after();
                 const uint32_t a_lo32 = (smA16 + sa * a_stage16) | a_lbo;
                 for (int kd = 0; kd < p.K; ++kd)
-                    for (int kh = 0; kh < p.K; ++kh)
-                        for (int kw = 0; kw < p.K; ++kw) {
-                            const uint32_t tap16 = (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
-                            mbar_wait(&b_full[sb], phb);
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint64_t db = ((uint64_t)b_hi32 << 32) | ((smB16 + sb * b_slot16) | b_lbo);
+                    for (int t0 = 0; t0 < p.K * p.K; t0 += p.TPS) {          // slot = TPS consecutive (kh, kw) taps of this kd
+                        mbar_wait(&b_full[sb], phb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            uint64_t db = ((uint64_t)b_hi32 << 32) | ((smB16 + sb * b_slot16) | b_lbo);
+                            int kh = t0 / p.K, kw = t0 - kh * p.K;
+                            for (int kk = 0; kk < p.TPS; ++kk, db += tapB16) {
+                                const uint32_t a_tap = a_lo32 + (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
 #pragma unroll
                                 for (int a = 0; a < AD; ++a) {
                                     if (NI == 2 && (a & 1) != me) continue;
-                                    const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (a_lo32 + tap16 + a * plane16);
+                                    const uint64_t da_hi = ((uint64_t)a_hi32 << 32) | (a_tap + a * plane16);
                                     tc_mma(dbase + (uint32_t)(a * P * N), da_hi, db, idesc1, acc_flag);
                                 }
                                 if (P == 2) {
 #pragma unroll
                                     for (int a = 0; a < AD; ++a) {
                                         if (NI == 2 && (a & 1) != me) continue;
-                                        const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (a_lo32 + a_prec16 + tap16 + a * plane16);
+                                        const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (a_tap + a_prec16 + a * plane16);
                                         tc_mma(dbase + (uint32_t)(a * P * N + N), da_lo, db, idesc2, 1u);
                                     }
                                 }
-                                tc_commit(&b_empty[sb]);              // weight slot free once these MMAs retire
+                                acc_flag = 1u;
+                                if (++kw == p.K) { kw = 0; ++kh; }
                             }
-                            __syncwarp();
-                            acc_flag = 1u;
-                            if (++sb == NB) { sb = 0; phb ^= 1; }
+                            tc_commit(&b_empty[sb]);                  // weight slot free once these MMAs retire
                         }
+                        __syncwarp();
+                        acc_flag = 1u;
+                        if (++sb == NB) { sb = 0; phb ^= 1; }
+                    }
                 if (elect_one()) tc_commit(&a_empty[sa]);
                 __syncwarp();
             }
@@ -542,7 +547,7 @@ static inline int ew_blocks(long long total) { return (int)std::min<long long>(c
 
 // ------------------------------------------------------------------------------------------------
 // host side: weight preparation, tensor maps, launches
-struct TileCfg { int AD, NB, persist; };          // d-planes per CTA, weight-ring depth, CTA scheduling (see conv_tc_launch_cfg)
+struct TileCfg { int AD, NB, persist, tps; };          // d-planes per CTA, weight-ring depth, CTA scheduling (see conv_tc_launch_cfg)
 struct TcVariant {                                 // [0] exact (P = 2), [1] fast (P = 1): own N tiling and weight image
     int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0};
     long long nt_woff[TC_MAX_NT] = {0, 0, 0, 0};
@@ -664,7 +669,7 @@ static void tune_file_load(TcState* st) {
     if (!f) return;
     int key, ad, nb; long long work;
     while (fscanf(f, "%d %d %d %lld", &key, &ad, &nb, &work) == 4)
-        if ((ad % 8) >= 1 && (ad % 8) <= 4 && nb >= 2 && nb <= 16) st->tuned[key] = std::make_pair(TileCfg{ad % 8, nb, ad / 8}, work);
+        if ((ad % 8) >= 1 && (ad % 8) <= 4 && (nb % 32) >= 2 && (nb % 32) <= 16) st->tuned[key] = std::make_pair(TileCfg{ad % 8, nb % 32, (ad / 8) % 4, nb / 32}, work);
     fclose(f);
 }
 static void tune_file_save(const TcState* st) {
@@ -672,7 +677,7 @@ static void tune_file_save(const TcState* st) {
     if (!path) return;
     FILE* f = fopen(path, "w");
     if (!f) return;
-    for (const auto& kv : st->tuned) fprintf(f, "%d %d %d %lld\n", kv.first, kv.second.first.AD + 8 * kv.second.first.persist, kv.second.first.NB, kv.second.second);
+    for (const auto& kv : st->tuned) fprintf(f, "%d %d %d %lld\n", kv.first, kv.second.first.AD + 8 * kv.second.first.persist, kv.second.first.NB + 32 * kv.second.first.tps, kv.second.second);
     fclose(f);
 }
 
@@ -690,7 +695,8 @@ static int get_encode(TcState* st) {
 static size_t tc_smem_bytes(const ConvUnit& cu, int Nmax, int P, TileCfg c) {
     const int pad = cu.dil * (cu.K / 2);
     const int PW = TC_TW + 2 * pad, HH = TC_TH + 2 * pad;
-    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P + (8 + 2 * c.NB) * 8 + 16;
+    const int tps = c.tps == 2 ? cu.K * cu.K : (c.tps == 1 ? cu.K : 1);
+    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P * tps + (8 + 2 * c.NB) * 8 + 16;
 }
 
 // feasible (d-planes per CTA, weight-ring depth) pairs: <= 512 TMEM columns (P accumulators per plane), <= 227 KB smem.
@@ -704,12 +710,15 @@ static std::vector<TileCfg> tile_candidates(const ConvUnit& cu, int Nmax, int S,
     std::vector<TileCfg> out;
     for (int ad = 1; ad <= ADmax; ++ad) {
         if ((double)S / (double)(cdiv(S, ad) * ad) < 0.85 && ad > 1) continue;       // too many planes outside the volume
-        for (int nb : {3, 6}) {
+        for (int nb : {2, 3, 6}) {
             if (env_nb && nb != env_nb) continue;
-            if (tc_smem_bytes(cu, Nmax, P, {ad, nb, 0}) <= 227 * 1024) { out.push_back({ad, nb, 0}); out.push_back({ad, nb, 1}); out.push_back({ad, nb, 2}); }
+            for (int tps = 0; tps <= (cu.K > 1 ? 2 : 0); ++tps) {
+                if ((nb == 2 && !tps) || (nb == 6 && tps)) continue;  // shallow rings only with multi-tap slots and vice versa
+                if (tc_smem_bytes(cu, Nmax, P, {ad, nb, 0, tps}) <= 227 * 1024) { out.push_back({ad, nb, 0, tps}); out.push_back({ad, nb, 1, tps}); out.push_back({ad, nb, 2, tps}); }
+            }
         }
     }
-    if (out.empty()) out.push_back({1, 2, 1});
+    if (out.empty()) out.push_back({1, 3, 1, 0});
     return out;
 }
 
@@ -736,7 +745,7 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     const int P = a.P, S = a.S;
     ConvTcParams p{};
     p.S = S; p.n_pc = a.n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.n_cblk = tu.Cin_pad / 16; p.cg_in = tu.Cin_pad / 8;
-    p.NB = cfg.NB;
+    p.NB = cfg.NB; p.TPS = cfg.tps == 2 ? cu.K * cu.K : (cfg.tps == 1 ? cu.K : 1);
     const int AD = cfg.AD;
     const int pad = cu.dil * (cu.K / 2);
     p.PW = TC_TW + 2 * pad; p.HH = TC_TH + 2 * pad; p.HD = AD + 2 * pad;
@@ -827,7 +836,7 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
                 if (ms < best) { best = ms; cfg = c; }
             }
             cudaEventDestroy(e0); cudaEventDestroy(e1);
-            if (getenv("SN_TC_VERBOSE")) fprintf(stderr, "[surfacenet_b200] tuned %s S=%d P=%d n=%d: AD=%d NB=%d persist=%d (%.3f ms)\n", kUnits[u].name, S, P, n_pc, cfg.AD, cfg.NB, cfg.persist, best / 2);
+            if (getenv("SN_TC_VERBOSE")) fprintf(stderr, "[surfacenet_b200] tuned %s S=%d P=%d n=%d: AD=%d NB=%d persist=%d tps=%d (%.3f ms)\n", kUnits[u].name, S, P, n_pc, cfg.AD, cfg.NB, cfg.persist, cfg.tps, best / 2);
         }
         st->tuned[key] = std::make_pair(cfg, work);
         tune_file_save(st);

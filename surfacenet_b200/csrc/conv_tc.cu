@@ -10,14 +10,18 @@
 // tap (kd,kh,kw) for the accumulator of plane a is base + (((a+kd*dil)*HH + kh*dil)*PW + kw*dil)*16 B.
 // No im2col copy is ever materialised; each input voxel is read from L2 ~2x per layer instead of 27x.
 //
-// One CTA owns AD accumulators in TMEM (each M = 128 voxels = 16 rows (h) x 8 (w) of one d-plane,
-// N = N_tile output channels, fp32), loops over 16-channel blocks (A ring, 2 stages) and taps (B = weight
-// ring, NB stages, 1-D bulk copies of pre-arranged canonical tiles) and issues, per (block, tap, plane),
-//   exact: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo      (fp16 2-term split of both operands; fp32 accumulate)
-//   fast : A_hi*W_hi
-// Warp roles: 0 = A producer (TMA), 1 = B producer (bulk copy), 2 = MMA issuer, 3 = TMEM allocator,
-// 4..7 = epilogue (TMEM -> registers -> folded BatchNorm + ReLU/sigmoid -> hi/lo split -> blk store, or the
-// fused merge_conv3 1x1x1 + sigmoid -> fp32 probability).
+// A CTA owns AD d-planes; each plane has an fp32 accumulator of M = 128 voxels (16 rows (h) x 8 (w)) x N output
+// channels in TMEM -- two of them side by side in exact mode, [main | corr].  It loops over 16-channel blocks (A ring,
+// 2 stages) and taps (B = weight ring of NB slots holding 1, K or K*K taps each, 1-D bulk copies of pre-arranged
+// canonical tiles) and issues, per (block, tap, plane),
+//   exact: [main | corr] += A_hi * [W_hi ; W_lo]^T (one N' = 2N MMA),  corr += A_lo * W_hi^T     (fp16 2-term split
+//          of both operands, fp32 accumulate; the epilogue adds main + corr)
+//   fast : main += A_hi * W_hi^T
+// The kernel is persistent (tile loop, optionally two TMEM accumulator sets so that the epilogue of one tile overlaps
+// the main loop of the next).  Warp roles: 0 = A producer (TMA), 1 = B producer (bulk copy), 2 (+3) = MMA issuers
+// (converged warp, one lane elected by elect.sync), 3 = TMEM allocator, 4..7 = epilogue (TMEM -> registers ->
+// folded BatchNorm + ReLU/sigmoid -> hi/lo split -> blk store, or the fused merge_conv3 1x1x1 + sigmoid -> fp32
+// probability).  The tile configuration (AD, NB, taps per slot, CTA scheduling) is measured once per unit.
 #include "net.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -630,7 +634,8 @@ int tc_prepare(Net& net) {
         // the folded BatchNorm multiplier puts that expected loss back (measured: 2.0e-8 per MMA).
         const double kRzLoss = 0.5 * 0.70 * ldexp(1.0, -23) * 0.5;
         static const int env_comp = getenv("SN_TC_RZCOMP") ? atoi(getenv("SN_TC_RZCOMP")) : 1;
-        const float comp = env_comp ? (float)(1.0 + kRzLoss * (double)n_cblk * K3) : 1.f;
+        static const double env_scale = getenv("SN_TC_RZSCALE") ? atof(getenv("SN_TC_RZSCALE")) : 1.0;
+        const float comp = env_comp ? (float)(1.0 + env_scale * kRzLoss * (double)n_cblk * K3) : 1.f;
         std::vector<float> sc(tu.Cout_pad, 0.f), sh(tu.Cout_pad, 0.f);
         for (int c = 0; c < cu.Cout; ++c) { sc[c] = cu.h_scale[c] * inv * comp; sh[c] = cu.h_shift[c]; }
         SN_CUDA(cudaMalloc((void**)&tu.scale, sc.size() * 4));

@@ -71,23 +71,92 @@ def append_dense_2sparseList(prediction_sub, rgb_sub, param_sub, viewPair_sub, m
                              enable_centerCrop=False, cube_Dcenter=None, enable_rayPooling=False, cameraPOs=None, cameraTs=None,
                              prediction_list=[], rgb_list=[], vxl_ijk_list=[], rayPooling_votes_list=[],
                              cube_ijk_np=None, param_np=None, viewPair_np=None):
-    """utils/sparseCubes.py:82 (same mutable-default signature; main_reconstruct.py always passes the lists)."""
-    prediction_sub = np.asarray(prediction_sub)
-    if prediction_sub.ndim == 5:
-        prediction_sub = prediction_sub.astype(np.float16)[:, 0]                           # sparseCubes.py:115
-    rgb_sub = np.transpose(np.asarray(rgb_sub).astype(np.uint8), axes=(0, 2, 3, 4, 1))     # sparseCubes.py:116
-    cube_ijk_sub = param_sub['ijk']
-    viewPair_sub = np.asarray(viewPair_sub).astype(np.uint16)
-    idx, ijk_l, pred_l, rgb_l, votes_l, param_new_sub = dense2sparse(
-        prediction=prediction_sub, rgb=rgb_sub, param=param_sub, viewPair=viewPair_sub, min_prob=min_prob, rayPool_thresh=rayPool_thresh,
-        enable_centerCrop=enable_centerCrop, cube_Dcenter=cube_Dcenter, enable_rayPooling=enable_rayPooling, cameraPOs=cameraPOs, cameraTs=cameraTs)
-    param_sub = param_new_sub[idx]
-    viewPair_sub = viewPair_sub[idx]
-    cube_ijk_sub = cube_ijk_sub[idx]
-    if not len(pred_l) == len(rgb_l) == len(ijk_l) == param_sub.shape[0] == viewPair_sub.shape[0] == cube_ijk_sub.shape[0]:
-        raise Warning('load dense data, # of cubes is not consistent.')                   # sparseCubes.py:131
-    prediction_list.extend(pred_l); rgb_list.extend(rgb_l); vxl_ijk_list.extend(ijk_l); rayPooling_votes_list.extend(votes_l)
-    param_np = param_sub if param_np is None else np.concatenate([param_np, param_sub], axis=0)
-    viewPair_np = viewPair_sub if viewPair_np is None else np.vstack([viewPair_np, viewPair_sub])
-    cube_ijk_np = cube_ijk_sub if cube_ijk_np is None else np.vstack([cube_ijk_np, cube_ijk_sub])
-    return prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list, cube_ijk_np, param_np, viewPair_np
+    """Same contract as utils/sparseCubes.py:82-141 (including the mutable default lists; main_reconstruct.py always passes
+    them): sparsify one dense batch on the GPU and append the non-empty cubes to the running lists / arrays."""
+    pred = np.asarray(prediction_sub)
+    if pred.ndim == 5:                                    # (N,1,D,D,D) float32 from the network -> (N,D,D,D) float16
+        pred = pred.astype(np.float16)[:, 0]
+    rgb_last = np.moveaxis(np.asarray(rgb_sub).astype(np.uint8), 1, -1)             # (N,3,D,D,D) -> (N,D,D,D,3)
+    pairs16 = np.asarray(viewPair_sub).astype(np.uint16)
+    kept, ijk_l, pred_l, rgb_l, votes_l, param_shifted = dense2sparse(
+        pred, rgb_last, param_sub, pairs16, min_prob=min_prob, rayPool_thresh=rayPool_thresh, enable_centerCrop=enable_centerCrop,
+        cube_Dcenter=cube_Dcenter, enable_rayPooling=enable_rayPooling, cameraPOs=cameraPOs, cameraTs=cameraTs)
+    new_param, new_pairs, new_ijk = param_shifted[kept], pairs16[kept], param_sub['ijk'][kept]
+    if len({len(pred_l), len(rgb_l), len(ijk_l), new_param.shape[0], new_pairs.shape[0], new_ijk.shape[0]}) != 1:
+        raise Warning('load dense data, # of cubes is not consistent.')
+    for dst, src in ((prediction_list, pred_l), (rgb_list, rgb_l), (vxl_ijk_list, ijk_l), (rayPooling_votes_list, votes_l)):
+        dst.extend(src)
+    stack = lambda old, new, fn: new if old is None else fn([old, new])
+    return (prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list,
+            stack(cube_ijk_np, new_ijk, np.vstack), stack(param_np, new_param, lambda x: np.concatenate(x, axis=0)),
+            stack(viewPair_np, new_pairs, np.vstack))
+
+
+# ---- host-side consumers of the sparse lists: thresholding masks and the on-disk NPZ schema ---------------------------
+NPZ_KEYS = ("cube_1st_vxlIndx_np", "prediction_np", "rgb_np", "vxl_ijk_np", "rayPooling_votes_np", "cube_ijk_np", "param_np", "viewPair_np")
+
+
+def _and_into(masks, new_masks):
+    """masks is extended when empty, otherwise and-ed element-wise in place (the reference's accumulate-or-create rule)."""
+    if not masks:
+        masks.extend(new_masks)
+    else:
+        for m, n in zip(masks, new_masks):
+            m &= n
+    return masks
+
+
+def filter_voxels(vxl_mask_list=[], prediction_list=None, prob_thresh=None, rayPooling_votes_list=None, rayPool_thresh=None):
+    """Same contract as utils/sparseCubes.py:205-243: per-cube boolean masks of `prediction >= prob_thresh` (scalar, or one
+    threshold per cube when a list is given) and `votes >= rayPool_thresh`, combined with the masks passed in."""
+    if prediction_list is not None:
+        if prob_thresh is None:
+            raise Warning('prob_thresh should not be None.')
+        per_cube = prob_thresh if isinstance(prob_thresh, list) else [prob_thresh] * len(prediction_list)
+        _and_into(vxl_mask_list, [p >= t for p, t in zip(prediction_list, per_cube)])
+    if rayPooling_votes_list is not None:
+        if rayPool_thresh is None:
+            raise Warning('rayPool_thresh should not be None.')
+        _and_into(vxl_mask_list, [v >= rayPool_thresh for v in rayPooling_votes_list])
+    return vxl_mask_list
+
+
+def save_sparseCubes(filePath, prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list, cube_ijk_np, param_np, viewPair_np):
+    """Writes the NPZ schema of utils/sparseCubes.py:330-366 (keys NPZ_KEYS; cube_1st_vxlIndx_np = uint32 start offsets, N+1)."""
+    starts = np.zeros(cube_ijk_np.shape[0] + 1, dtype=np.uint32)
+    sizes = np.fromiter((p.size for p in prediction_list), dtype=np.uint32, count=len(prediction_list))
+    starts[1:1 + sizes.size] = np.cumsum(sizes, dtype=np.uint32)
+    flat = dict(prediction_np=np.concatenate(prediction_list, axis=0), rgb_np=np.vstack(rgb_list), vxl_ijk_np=np.vstack(vxl_ijk_list),
+                rayPooling_votes_np=np.concatenate(rayPooling_votes_list, axis=0) if rayPooling_votes_list else np.empty((0,), np.uint8))
+    if not starts[-1] == flat["prediction_np"].shape[0] == flat["rgb_np"].shape[0] == flat["vxl_ijk_np"].shape[0]:
+        raise Warning("# of voxels is not consistent while saving sparseCubes.")
+    with open(filePath, 'wb') as f:
+        np.savez_compressed(f, cube_1st_vxlIndx_np=starts, cube_ijk_np=cube_ijk_np, param_np=param_np, viewPair_np=viewPair_np, **flat)
+
+
+def load_sparseCubes(filePath):
+    """Reads that schema back (utils/sparseCubes.py:369-405)
+    -> prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list, cube_ijk_np, param_np, viewPair_np"""
+    with np.load(filePath) as npz:
+        z = {k: npz[k] for k in NPZ_KEYS}
+    starts, n_vox = z["cube_1st_vxlIndx_np"].astype(np.int64), int(z["cube_1st_vxlIndx_np"][-1])
+    if not n_vox == z["prediction_np"].shape[0] == z["rgb_np"].shape[0] == z["vxl_ijk_np"].shape[0]:
+        raise Warning("# of voxels is not consistent while saving sparseCubes.")
+    if z["rayPooling_votes_np"].shape[0] not in (0, n_vox):
+        raise Warning("rayPooling_votes_np.shape[0] != 0 / # of voxels.")
+    n_cube = z["cube_ijk_np"].shape[0]
+    cut = lambda a: [a[starts[i]:starts[i + 1]] for i in range(n_cube)]
+    return (cut(z["prediction_np"]), cut(z["rgb_np"]), cut(z["vxl_ijk_np"]), cut(z["rayPooling_votes_np"]),
+            z["cube_ijk_np"], z["param_np"], z["viewPair_np"])
+
+
+def lists_from_flat(sparse, param_sub, viewPair_sub, cube_Dcenter, D):
+    """Turn the flat output of HotPath.infer_batch_sparse into exactly what append_dense_2sparseList would have appended:
+    (prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list, cube_ijk_np, param_np, viewPair_np) of the non-empty cubes,
+    with the centre-crop shift of the cube origin applied (sparseCubes.py:55)."""
+    off = sparse["offsets"]
+    idx = [n for n in range(len(sparse["counts"])) if sparse["counts"][n] > 0]
+    param_new = np.copy(param_sub)
+    param_new['xyz'] += param_new['resol'][:, None] * ((D - cube_Dcenter) // 2)
+    return (_split(sparse["pred"], off, idx), _split(sparse["rgb"], off, idx), _split(sparse["ijk"], off, idx),
+            _split(sparse["votes"], off, idx), param_sub['ijk'][idx], param_new[idx], np.asarray(viewPair_sub).astype(np.uint16)[idx])

@@ -152,3 +152,67 @@ def test_bench_reference_arm_json():
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "voxels/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+def _ref_sparse_funcs():
+    """filter_voxels / save_sparseCubes / load_sparseCubes executed from the reference source when it is present (build
+    container only); mechanical py3 fix: np.load needs a binary file handle (`open(filePath)` -> `open(filePath, 'rb')`)."""
+    ref = "/root/reference/utils/sparseCubes.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not present")
+    src = open(ref).read()
+    a, b, c = src.index("def filter_voxels("), src.index("def save2ply("), src.index("def save_sparseCubes(")
+    d = src.index("def __debug():")
+    body = (src[a:b] + src[c:d]).replace("with open(filePath) as f:", "with open(filePath, 'rb') as f:")
+    ns = {"np": np}
+    exec(compile(body, ref, "exec"), ns)
+    return ns
+
+
+def test_sparse_host_consumers_match_reference(tmp_path, capsys):
+    from surfacenet_b200 import sparseCubes
+    ns = _ref_sparse_funcs()
+    rs = np.random.RandomState(3)
+    counts = [5, 0, 17, 3]
+    pl = [rs.rand(n).astype(np.float16) for n in counts]
+    rl = [rs.randint(0, 256, (n, 3)).astype(np.uint8) for n in counts]
+    il = [rs.randint(0, 52, (n, 3)).astype(np.uint8) for n in counts]
+    vl = [rs.randint(0, 11, n).astype(np.uint8) for n in counts]
+    cube_ijk = rs.randint(0, 40, (4, 3)).astype(np.uint32)
+    param = np.zeros(4, util.PARAM_DTYPE); param["xyz"] = rs.rand(4, 3); param["resol"] = 0.4
+    vp = rs.randint(0, 49, (4, 5, 2)).astype(np.uint16)
+    # masks
+    m_ref = ns["filter_voxels"]([], pl, 0.7, vl, 8.0)
+    m_new = sparseCubes.filter_voxels([], pl, 0.7, vl, 8.0)
+    assert all(np.array_equal(a, b) for a, b in zip(m_ref, m_new)) and len(m_new) == 4
+    m_new2 = sparseCubes.filter_voxels([m.copy() for m in m_new], prediction_list=pl, prob_thresh=[0.9, 0.1, 0.5, 0.2])
+    m_ref2 = ns["filter_voxels"]([m.copy() for m in m_ref], prediction_list=pl, prob_thresh=[0.9, 0.1, 0.5, 0.2])
+    assert all(np.array_equal(a, b) for a, b in zip(m_ref2, m_new2))
+    with pytest.raises(Warning):
+        sparseCubes.filter_voxels([], pl, None)
+    # NPZ schema: written by us -> read by the reference, and the other way round
+    f1, f2 = str(tmp_path / "a.npz"), str(tmp_path / "b.npz")
+    sparseCubes.save_sparseCubes(f1, pl, rl, il, vl, cube_ijk, param, vp)
+    ns["save_sparseCubes"](f2, pl, rl, il, vl, cube_ijk, param, vp)
+    z1, z2 = np.load(f1), np.load(f2)
+    assert sorted(z1.files) == sorted(z2.files) and all(np.array_equal(z1[k], z2[k]) and z1[k].dtype == z2[k].dtype for k in z1.files)
+    back_ref = ns["load_sparseCubes"](f1)
+    back_new = sparseCubes.load_sparseCubes(f2)
+    for a, b in zip(back_ref, back_new):
+        if isinstance(a, list):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        else:
+            assert np.array_equal(a, b)
+    assert all(np.array_equal(x, y) for x, y in zip(back_new[0], pl))
+
+
+def test_lists_from_flat():
+    from surfacenet_b200 import sparseCubes
+    counts = np.array([2, 0, 3], np.int32)
+    sp = dict(counts=counts, offsets=np.array([0, 2, 2, 5], np.int32), pred=np.arange(5).astype(np.float16), rgb=np.zeros((5, 3), np.uint8),
+              ijk=np.arange(15).reshape(5, 3).astype(np.uint8), votes=np.arange(5).astype(np.uint8))
+    param = np.zeros(3, util.PARAM_DTYPE); param["xyz"] = 10.0; param["resol"] = 0.5; param["ijk"] = np.arange(9).reshape(3, 3)
+    vp = np.arange(12).reshape(3, 2, 2)
+    pl, rl, il, vl, cube_ijk, param_np, vp_np = sparseCubes.lists_from_flat(sp, param, vp, 52, 64)
+    assert [len(x) for x in pl] == [2, 3] and np.array_equal(il[1], sp["ijk"][2:5]) and np.array_equal(vl[1], [2, 3, 4])
+    assert np.array_equal(cube_ijk, param["ijk"][[0, 2]]) and np.allclose(param_np["xyz"], 10.0 + 0.5 * 6) and vp_np.dtype == np.uint16

@@ -1,0 +1,76 @@
+"""The SurfaceNet-inference section of main_reconstruct.reconstruction (main_reconstruct.py:119-183) on top of the fused hot
+path: batches of cubes go through HotPath.infer_batch_sparse (CVC -> SurfaceNet -> fusion -> colours -> ray-pool votes ->
+centre crop / threshold / compaction, all on the GPU), the per-cube sparse lists are accumulated exactly as
+sparseCubes.append_dense_2sparseList would, thresholded with (tau, gamma) and written in the reference's NPZ schema.
+
+What comes BEFORE this section in the reference (image / camera loading, early rejection with similarityNet, view-pair
+selection) is out of scope: the caller passes the selected view pairs and their weights.
+"""
+import math
+import numpy as np
+from . import sparseCubes
+from .pipeline import HotPath
+
+PARAM_DTYPE = np.dtype([("xyz", np.float32, (3,)), ("ijk", np.uint32, (3,)), ("resol", np.float32)])      # utils/scene.py:55
+CUBE_DCENTER = {32: 26, 64: 52}            # params.py:107
+TAU, GAMMA, MIN_PROB = 0.7, 0.8, 0.46      # params.py:66-68
+
+
+def initialize_cubes(resol, cube_D, cube_Dcenter, cube_overlapping_ratio, BB):
+    """Overlapping cube grid over the bounding box BB = [[x_min,x_max],[y_min,y_max],[z_min,z_max]], same layout as
+    utils/scene.py:7-61 (stride = Dcenter * resol * overlap, first cube at BB_min - (D - Dcenter) * resol / 2, ijk C-order)."""
+    BB = np.asarray(BB, dtype=np.float64)
+    side, centre = resol * cube_D, resol * cube_Dcenter
+    stride, margin = centre * cube_overlapping_ratio, (side - centre) / 2
+    n_axis = [int(math.ceil(((BB[a][1] + margin) - (BB[a][0] - margin)) / stride)) for a in range(3)]
+    ijk = np.indices(tuple(n_axis)).reshape(3, -1).T
+    cubes = np.empty(ijk.shape[0], dtype=PARAM_DTYPE)
+    cubes["ijk"] = ijk
+    cubes["xyz"] = ijk * stride + (BB[:, 0][None, :] - margin)
+    cubes["resol"] = resol
+    return cubes, side
+
+
+def reconstruct_cubes(hot, cubes_param, viewPairs, w, cube_D, cube_Dcenter=None, batch_size=16, rayPool_thresh=0,
+                      rank=0, world_size=1, progress=None):
+    """main_reconstruct.py:119-166.  hot: pipeline.HotPath; cubes_param: structured array ('xyz','ijk','resol') of the valid
+    cubes; viewPairs (N, N_vp, 2) int; w (N, N_vp) float32 (ignored when N_vp == 1).  With world_size > 1 the batches are
+    dealt round-robin to the ranks (cubes are independent) and every rank returns ITS cubes only.
+    -> (prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list, cube_ijk_np, param_np, viewPair_np) or "Empty!"."""
+    Dc = int(cube_Dcenter if cube_Dcenter is not None else CUBE_DCENTER.get(int(cube_D), cube_D))
+    N = len(cubes_param)
+    if N == 0:
+        return "Empty!"                                                # main_reconstruct.py:128-129
+    viewPairs = np.asarray(viewPairs)
+    n_vp = viewPairs.shape[1]
+    lists = ([], [], [], [])
+    cube_ijk_np = param_np = viewPair_np = None
+    starts = list(range(0, N, batch_size))[rank::world_size]
+    for i, b0 in enumerate(starts):
+        sel = slice(b0, min(N, b0 + batch_size))
+        sp = hot.infer_batch_sparse(viewPairs[sel], cubes_param["xyz"][sel], cubes_param["resol"][sel],
+                                    None if n_vp == 1 else np.asarray(w)[sel], cube_D, Dc, rayPool_thresh)
+        pl, rl, il, vl, ijk_b, param_b, vp_b = sparseCubes.lists_from_flat(sp, cubes_param[sel], viewPairs[sel], Dc, cube_D)
+        for dst, src in zip(lists, (pl, rl, il, vl)):
+            dst.extend(src)
+        if len(pl):
+            cube_ijk_np = ijk_b if cube_ijk_np is None else np.vstack([cube_ijk_np, ijk_b])
+            param_np = param_b if param_np is None else np.concatenate([param_np, param_b], axis=0)
+            viewPair_np = vp_b if viewPair_np is None else np.vstack([viewPair_np, vp_b])
+        if progress is not None:
+            progress(i + 1, len(starts))
+    if cube_ijk_np is None:
+        return "Empty!"
+    return lists + (cube_ijk_np, param_np, viewPair_np)
+
+
+def finish(result, npz_path=None, tau=TAU, gamma=GAMMA):
+    """main_reconstruct.py:170-183 without the cross-cube denoising and the PLY writer (out of scope): the fixed-threshold
+    mask `prediction >= tau & votes >= gamma * N_vp * 2`, and the NPZ file adapthresh / load_sparseCubes read back."""
+    prediction_list, rgb_list, vxl_ijk_list, votes_list, cube_ijk_np, param_np, viewPair_np = result
+    n_vp = viewPair_np.shape[1]
+    masks = sparseCubes.filter_voxels(vxl_mask_list=[], prediction_list=prediction_list, prob_thresh=tau,
+                                      rayPooling_votes_list=votes_list, rayPool_thresh=gamma * n_vp * 2)
+    if npz_path is not None:
+        sparseCubes.save_sparseCubes(npz_path, *result)
+    return masks

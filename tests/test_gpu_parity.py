@@ -458,3 +458,39 @@ def test_infer_batch_sparse_matches_dense_pipeline(torch_cuda, params, cams):
     assert sp["counts"].sum() == sum(len(x) for x in pl) > 0
     assert np.array_equal(sp["pred"], np.concatenate(pl)) and np.array_equal(sp["ijk"], np.concatenate(il))
     assert np.array_equal(sp["rgb"], np.concatenate(rl)) and np.array_equal(sp["votes"], np.concatenate(vl))
+
+
+def test_reconstruct_cubes_batching_and_npz(torch_cuda, params, cams, tmp_path):
+    """The inference section of main_reconstruct.reconstruction over a small cube grid: batched == one call, ranks
+    partition the cubes, NPZ round trip in the reference schema."""
+    from surfacenet_b200 import SurfaceNet, pipeline, reconstruct, sparseCubes
+    from surfacenet_b200.device import DeviceScene
+    D, Dc = 16, 12
+    cubes, side = reconstruct.initialize_cubes(np.float32(0.4), D, Dc, 0.5, np.array([[10, 14], [-30, -26], [620, 624]]))
+    assert side == np.float32(0.4) * D and len(cubes) > 20 and np.array_equal(cubes["ijk"][1], [0, 0, 1])
+    cubes = cubes[::4][:7]
+    rs = np.random.RandomState(2)
+    used = [8, 9, 22, 23]
+    imgs = util.image_list(49, used)
+    pairs = rs.choice(used, size=(len(cubes), 2, 2))
+    w = (rs.rand(len(cubes), 2) + 0.1).astype(np.float32)
+    hot = pipeline.HotPath(SurfaceNet.Net(params), DeviceScene(cams, imgs), mode="exact")
+    res = reconstruct.reconstruct_cubes(hot, cubes, pairs, w, D, Dc, batch_size=3)
+    one = hot.infer_batch_sparse(pairs, cubes["xyz"], cubes["resol"], w, D, Dc)
+    ref = sparseCubes.lists_from_flat(one, cubes, pairs, Dc, D)
+    assert len(res[0]) == len(ref[0]) > 0
+    for a, b in zip(res, ref):
+        if isinstance(a, list):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        else:
+            assert np.array_equal(a, b)
+    # two "ranks" see disjoint cubes whose union is everything
+    parts = [reconstruct.reconstruct_cubes(hot, cubes, pairs, w, D, Dc, batch_size=2, rank=r, world_size=2) for r in range(2)]
+    got = sorted(tuple(x) for p in parts if p != "Empty!" for x in p[4].tolist())
+    assert got == sorted(tuple(x) for x in ref[4].tolist())
+    f = str(tmp_path / "model.npz")
+    masks = reconstruct.finish(res, f)
+    back = sparseCubes.load_sparseCubes(f)
+    assert all(np.array_equal(x, y) for x, y in zip(back[0], res[0])) and np.array_equal(back[5]["xyz"], res[5]["xyz"])
+    assert len(masks) == len(res[0]) and masks[0].dtype == bool
+    assert reconstruct.reconstruct_cubes(hot, cubes[:0], pairs[:0], w[:0], D, Dc) == "Empty!"

@@ -216,3 +216,16 @@ def test_lists_from_flat():
     pl, rl, il, vl, cube_ijk, param_np, vp_np = sparseCubes.lists_from_flat(sp, param, vp, 52, 64)
     assert [len(x) for x in pl] == [2, 3] and np.array_equal(il[1], sp["ijk"][2:5]) and np.array_equal(vl[1], [2, 3, 4])
     assert np.array_equal(cube_ijk, param["ijk"][[0, 2]]) and np.allclose(param_np["xyz"], 10.0 + 0.5 * 6) and vp_np.dtype == np.uint16
+
+
+def test_initialize_cubes_matches_reference_log():
+    """utils/scene.py:43-58 on DTU scan9 (params.py:161-172): the shipped job log reports 24,420 cubes at s=64
+    (q.log/inference.0000022:116); s=32 gives 40 x 74 x 66."""
+    from surfacenet_b200 import reconstruct
+    BB = np.array([[-73, 129], [-197, 183], [472, 810]])
+    c, side = reconstruct.initialize_cubes(np.float32(0.4), 64, 52, 0.5, BB)
+    assert len(c) == 24420 and np.array_equal(c["ijk"].max(0) + 1, [20, 37, 33]) and abs(side - 25.6) < 1e-5
+    assert np.allclose(c["xyz"][0], BB[:, 0] - (64 - 52) * 0.4 / 2, atol=1e-5) and np.array_equal(c["ijk"][1], [0, 0, 1])
+    assert np.allclose(c["xyz"][1] - c["xyz"][0], [0, 0, 52 * 0.4 * 0.5], atol=1e-5)
+    c, _ = reconstruct.initialize_cubes(np.float32(0.4), 32, 26, 0.5, BB)
+    assert len(c) == 40 * 74 * 66

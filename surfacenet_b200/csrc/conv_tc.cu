@@ -891,12 +891,15 @@ static long long tc_halfs_per_pc(int D) {
     const long long V = (long long)D * D * D, V2 = V / 8, V4 = V / 64;
     return V * (16 + 32 + 32 + 64 + 112) + V2 * (32 + 80 + 80 + 16) + V4 * (80 + 160 + 160 + 16 + 304 + 304 + 16);
 }
-constexpr int kTcMaxChunk = 64;
+constexpr int kTcMaxChunk = 128;     // pair-cubes per forward chunk: 312 MB of activations each at 64^3 (exact) -> <= 40 GB
+
+// equal-sized chunks (80 -> 80, 200 -> 100 + 100) so that no small tail chunk runs at poor occupancy
+static int tc_chunk(int n_pc) { return n_pc <= 0 ? 0 : (int)cdiv(n_pc, cdiv(n_pc, kTcMaxChunk)); }
 
 int64_t tc_workspace_bytes(const Net& net, int n_pc, int D, int mode) {
     (void)net;
     const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
-    return align_up(tc_halfs_per_pc(D) * 2 * P * std::min(n_pc, kTcMaxChunk), 256) + 4096;
+    return align_up(tc_halfs_per_pc(D) * 2 * P * tc_chunk(n_pc), 256) + 4096;
 }
 
 static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float* prob_out, __half* ws, int P, cudaStream_t st) {
@@ -945,7 +948,7 @@ int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out,
     const int64_t need = tc_workspace_bytes(net, n_pc, D, mode);
     if (!ws || ws_bytes < need) { set_error("tensor-core forward: workspace %lld B < %lld B", (long long)ws_bytes, (long long)need); return SN_ERR_NOMEM; }
     const long long V = (long long)D * D * D;
-    const int chunk = std::min(n_pc, kTcMaxChunk);
+    const int chunk = tc_chunk(n_pc);
     __half* w = (__half*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     for (int i = 0; i < n_pc; i += chunk) {
         const int n = std::min(chunk, n_pc - i);

@@ -124,6 +124,10 @@ struct ConvTcParams {
     int act, epi;
     // EPI_BLK
     __half* out; int cg_out_total, cg_out_off;
+    // optional fused 1x1x1 side output (16 channels) + BatchNorm + sigmoid on this unit's activation   SurfaceNet.py:38,47
+    const float* side_w;            // [C_out_pad][16] fp32 (transposed), NULL = no side output
+    const float* side_scale; const float* side_shift;
+    __half* side_out; int side_cg_total, side_cg_off;
     // EPI_FINAL: fused merge_conv3 (1x1x1, C -> 1) + BatchNorm + sigmoid      SurfaceNet.py:74
     const float* w3; float scale3, shift3; int c3; float* prob_out;
 };
@@ -175,10 +179,13 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvTcParams& p, uint32_t 
 }
 
 // co-resident CTAs the register allocation must allow: small fast-mode CTAs share an SM four at a time
-template <int AD, int P> struct TcMinBlocks { static constexpr int value = (P == 1) ? (AD == 1 ? 4 : (AD == 2 ? 2 : 1)) : (AD == 1 ? 2 : 1); };
+template <int AD, int P, bool SIDE> struct TcMinBlocks {
+    static constexpr int base = (P == 1) ? (AD == 1 ? 4 : (AD == 2 ? 2 : 1)) : (AD == 1 ? 2 : 1);
+    static constexpr int value = SIDE ? 2 : base;                        // fused side output: cap the epilogue at 128 registers, no more, no less
+};
 
-template <int AD, int P>
-__global__ void __launch_bounds__(TC_THREADS, TcMinBlocks<AD, P>::value)
+template <int AD, int P, bool SIDE>
+__global__ void __launch_bounds__(TC_THREADS, TcMinBlocks<AD, P, SIDE>::value)
 conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -348,6 +355,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                 const long long vox = ((long long)d * S + h) * S + w;
                 const uint32_t trow = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P * N);
                 float z = 0.f;
+                float sacc[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) sacc[o] = 0.f;
 #pragma unroll 1
                 for (int jc = 0; jc < N; jc += 16) {
                     uint32_t v[16];
@@ -366,6 +376,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                     for (int i = 0; i < 16; ++i) {
                         const int ch = c_base + jc + i;
                         y[i] = tc_act(fmaf(__uint_as_float(v[i]), __ldg(p.scale + ch), __ldg(p.shift + ch)), p.act);
+                    }
+                    if (SIDE) {                                               // side_op: 16 outputs from this voxel's channels, fp32
+#pragma unroll
+                        for (int i0 = 0; i0 < 16; i0 += 4) {
+#pragma unroll
+                            for (int i = i0; i < i0 + 4; ++i) {
+                                const float4* wr = reinterpret_cast<const float4*>(p.side_w + (size_t)(c_base + jc + i) * 16);
+                                const float yi = y[i];
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    const float4 w4 = __ldg(wr + q4);
+                                    sacc[4 * q4 + 0] = fmaf(yi, w4.x, sacc[4 * q4 + 0]);
+                                    sacc[4 * q4 + 1] = fmaf(yi, w4.y, sacc[4 * q4 + 1]);
+                                    sacc[4 * q4 + 2] = fmaf(yi, w4.z, sacc[4 * q4 + 2]);
+                                    sacc[4 * q4 + 3] = fmaf(yi, w4.w, sacc[4 * q4 + 3]);
+                                }
+                            }
+                            asm volatile("" ::: "memory");                   // keep the weight loads of one group of 4 channels in flight, not all 64
+                        }
                     }
                     if (p.epi == EPI_FINAL) {
 #pragma unroll
@@ -391,6 +420,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                 }
                 if (p.epi == EPI_FINAL && ok)
                     p.prob_out[(long long)c.pc * vol + vox] = 1.f / (1.f + expf(-fmaf(z, p.scale3, p.shift3)));
+                if (SIDE && ok) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        __half hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int o = 8 * g + i;
+                            const float sv = 1.f / (1.f + expf(-fmaf(sacc[o], __ldg(p.side_scale + o), __ldg(p.side_shift + o))));
+                            hi[i] = __float2half_rn(sv);
+                            lo[i] = __float2half_rn(sv - __half2float(hi[i]));
+                        }
+                        __half* dst = p.side_out + (((long long)c.pc * P) * p.side_cg_total + p.side_cg_off + g) * vol * 8 + vox * 8;
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+                        if (P == 2)
+                            *reinterpret_cast<uint4*>(dst + (long long)p.side_cg_total * vol * 8) =
+                                make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+                    }
+                }
             }
             tc_fence_before();                                             // TMEM reads done -> the MMA warp may overwrite this set
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
@@ -559,6 +606,7 @@ struct TcVariant {                                 // [0] exact (P = 2), [1] fas
 };
 struct TcUnit {
     int Cin_pad = 0, Cout_pad = 0, taps = 0;
+    float* side_w = nullptr;                       // for side units with one-N-tile producers: [Cin_pad][16] fp32 (transposed)
     TcVariant v[2];
     float* scale = nullptr;                        // Cout_pad entries, zero for padded channels
     float* shift = nullptr;
@@ -643,6 +691,15 @@ int tc_prepare(Net& net) {
         SN_CUDA(cudaMemcpy(tu.scale, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
         SN_CUDA(cudaMemcpy(tu.shift, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice));
     }
+    for (int u : {U_SIDE1, U_SIDE2}) {             // side outputs that can ride in their producer's epilogue (SurfaceNet.py:38,47)
+        const ConvUnit& su = net.units[u];
+        TcUnit& tu = st->units[u];
+        std::vector<float> wt((size_t)pad16(su.Cin) * 16, 0.f);
+        for (int o = 0; o < su.Cout; ++o)
+            for (int c = 0; c < su.Cin; ++c) wt[(size_t)c * 16 + o] = su.h_w[(size_t)o * su.Cin + c];
+        SN_CUDA(cudaMalloc((void**)&tu.side_w, wt.size() * 4));
+        SN_CUDA(cudaMemcpy(tu.side_w, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+    }
     {   // merge_conv3 for the fused epilogue of merge_conv2
         const ConvUnit& m3 = net.units[U_MERGE3];
         std::vector<float> w3(pad16(m3.Cin), 0.f);
@@ -659,6 +716,7 @@ void tc_destroy(Net& net) {
     if (!st) return;
     for (int u = 0; u < kNumUnits; ++u) {
         cudaFree(st->units[u].v[0].w); cudaFree(st->units[u].v[1].w); cudaFree(st->units[u].scale); cudaFree(st->units[u].shift);
+        cudaFree(st->units[u].side_w);
     }
     cudaFree(st->w3);
     delete st;
@@ -727,19 +785,20 @@ static std::vector<TileCfg> tile_candidates(const ConvUnit& cu, int Nmax, int S,
     return out;
 }
 
-template <int AD, int P>
+template <int AD, int P, bool SIDE>
 static int conv_tc_launch_t(const CUtensorMap& map, const ConvTcParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        SN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<AD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SN_CUDA((cudaFuncSetAttribute(conv_tc_kernel<AD, P, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
         attr_set = true;
     }
-    conv_tc_kernel<AD, P><<<grid, TC_THREADS, smem, stream>>>(map, p);
+    conv_tc_kernel<AD, P, SIDE><<<grid, TC_THREADS, smem, stream>>>(map, p);
     return SN_OK;
 }
 
 struct TcLaunchArgs {
     const Net* net; int u; const __half* in; int n_pc, S, P, epi; __half* out; int cg_out_total, cg_out_off; float* prob_out;
+    int side_unit; __half* side_out; int side_cg_total, side_cg_off;          // side_unit < 0: no fused side output
 };
 
 static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t stream) {
@@ -762,6 +821,12 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     p.weights = tv.w; p.scale = tu.scale; p.shift = tu.shift; p.act = cu.act; p.epi = a.epi;
     p.out = a.out; p.cg_out_total = a.cg_out_total; p.cg_out_off = a.cg_out_off;
     p.w3 = st->w3; p.scale3 = st->scale3; p.shift3 = st->shift3; p.c3 = a.net->units[U_MERGE3].Cin; p.prob_out = a.prob_out;
+    if (a.side_unit >= 0) {
+        SN_CHECK_ARG(tv.n_ntiles == 1 && st->units[a.side_unit].side_w && a.net->units[a.side_unit].Cin == cu.Cout,
+                     "conv_tc: unit %s cannot carry the side output %s", kUnits[a.u].name, kUnits[a.side_unit].name);
+        p.side_w = st->units[a.side_unit].side_w; p.side_scale = a.net->units[a.side_unit].scale; p.side_shift = a.net->units[a.side_unit].shift;
+        p.side_out = a.side_out; p.side_cg_total = a.side_cg_total; p.side_cg_off = a.side_cg_off;
+    }
 
     CUtensorMap map;
     const cuuint64_t gdim[4] = {(cuuint64_t)8 * S, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)a.n_pc * P * p.cg_in};
@@ -791,7 +856,8 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     SN_CHECK_ARG(p.n_tiles <= 0x7fffffff, "conv_tc: too many tiles (%lld)", p.n_tiles);
     dim3 grid((unsigned)(cfg.persist ? std::min<long long>(p.n_tiles, (long long)n_sm * per_sm) : p.n_tiles));
     int rc = SN_ERR_INVALID;
-#define SN_TC_CASE(ad, pp) if (AD == ad && P == pp) rc = conv_tc_launch_t<ad, pp>(map, p, grid, smem_launch, stream)
+#define SN_TC_CASE(ad, pp) if (AD == ad && P == pp) rc = p.side_w ? conv_tc_launch_t<ad, pp, true>(map, p, grid, smem_launch, stream) \
+                                                                    : conv_tc_launch_t<ad, pp, false>(map, p, grid, smem_launch, stream)
     SN_TC_CASE(1, 1); SN_TC_CASE(2, 1); SN_TC_CASE(3, 1); SN_TC_CASE(4, 1);
     SN_TC_CASE(1, 2); SN_TC_CASE(2, 2); SN_TC_CASE(3, 2); SN_TC_CASE(4, 2);
 #undef SN_TC_CASE
@@ -802,7 +868,8 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
 
 // in: blk (n_pc, P, Cin_pad/8, S^3, 8).  EPI_BLK: out blk with cg_out_total groups, written at cg_out_off.
 static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int S, int P, int epi, __half* out, int cg_out_total,
-                          int cg_out_off, float* prob_out, cudaStream_t stream) {
+                          int cg_out_off, float* prob_out, cudaStream_t stream, int side_unit = -1, __half* side_out = nullptr,
+                          int side_cg_total = 0, int side_cg_off = 0) {
     TcState* st = (TcState*)net.tc;
     const ConvUnit& cu = net.units[u];
     const TcVariant& tv = st->units[u].v[(P == 2) ? 0 : 1];
@@ -811,12 +878,12 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
     SN_CHECK_ARG(epi != EPI_FINAL || tv.n_ntiles == 1, "conv_tc: the fused merge_conv3 epilogue needs all channels in one N tile");
     int Nmax = 0;
     for (int t = 0; t < tv.n_ntiles; ++t) Nmax = std::max(Nmax, tv.nt_size[t]);
-    const TcLaunchArgs args{&net, u, in, n_pc, S, P, epi, out, cg_out_total, cg_out_off, prob_out};
+    const TcLaunchArgs args{&net, u, in, n_pc, S, P, epi, out, cg_out_total, cg_out_off, prob_out, side_unit, side_out, side_cg_total, side_cg_off};
 
     // one-time measurement of the tile configuration per (unit, S, mode); the timed launches rewrite the same output
     static const int env_tune = getenv("SN_TC_TUNE") ? atoi(getenv("SN_TC_TUNE")) : 1;
     const long long work = (long long)n_pc * S * S * S;
-    const int key = (u * 2 + (P == 2 ? 0 : 1)) * 1024 + std::min(S, 1023);
+    const int key = ((u + (side_unit >= 0 ? 32 : 0)) * 2 + (P == 2 ? 0 : 1)) * 1024 + std::min(S, 1023);
     auto it = st->tuned.find(key);
     TileCfg cfg;
     if (it != st->tuned.end() && (it->second.second >= work || !env_tune)) {
@@ -911,19 +978,20 @@ static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float*
     __half* s2 = b2 + 80 * V2 * np; __half* p2 = s2 + 16 * V2 * np; __half* c1 = p2 + 80 * V4 * np; __half* c2 = c1 + 160 * V4 * np;
     __half* s3 = c2 + 160 * V4 * np; __half* d1 = s3 + 16 * V4 * np; __half* d2 = d1 + 304 * V4 * np; __half* s4 = d2 + 304 * V4 * np;
     const ConvUnit* U = net.units;
+    static const bool fuse_side = getenv("SN_TC_FUSE_SIDE") ? atoi(getenv("SN_TC_FUSE_SIDE")) != 0 : true;
     int rc;
 #define RUN(x) do { rc = (x); if (rc != SN_OK) return rc; } while (0)
 #define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))
     RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
     CONV(U_CONV1_1, x0, S1, a1, 4, 0);
     CONV(U_CONV1_2, a1, S1, a2, 4, 0);
-    CONV(U_CONV1_3, a2, S1, a1, 4, 0);
-    CONV(U_SIDE1, a1, S1, cat, 8, 0);                                             // side_op1 -> concat[0:16]
+    if (fuse_side) RUN(conv_tc_launch(net, U_CONV1_3, a2, n, S1, P, EPI_BLK, a1, 4, 0, nullptr, st, U_SIDE1, cat, 8, 0));   // + side_op1 -> concat[0:16]
+    else { CONV(U_CONV1_3, a2, S1, a1, 4, 0); CONV(U_SIDE1, a1, S1, cat, 8, 0); }
     RUN(pool_launch(a1, n, 32, P, S1, p1, st));
     CONV(U_CONV2_1, p1, S2, b1, 10, 0);
     CONV(U_CONV2_2, b1, S2, b2, 10, 0);
-    CONV(U_CONV2_3, b2, S2, b1, 10, 0);
-    CONV(U_SIDE2, b1, S2, s2, 2, 0);
+    if (fuse_side) RUN(conv_tc_launch(net, U_CONV2_3, b2, n, S2, P, EPI_BLK, b1, 10, 0, nullptr, st, U_SIDE2, s2, 2, 0));    // + side_op2
+    else { CONV(U_CONV2_3, b2, S2, b1, 10, 0); CONV(U_SIDE2, b1, S2, s2, 2, 0); }
     RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, st));   // -> concat[16:32]
     RUN(pool_launch(b1, n, 80, P, S2, p2, st));
     CONV(U_CONV3_1, p2, S4, c1, 20, 0);

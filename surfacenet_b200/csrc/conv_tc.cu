@@ -978,7 +978,10 @@ static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float*
     __half* s2 = b2 + 80 * V2 * np; __half* p2 = s2 + 16 * V2 * np; __half* c1 = p2 + 80 * V4 * np; __half* c2 = c1 + 160 * V4 * np;
     __half* s3 = c2 + 160 * V4 * np; __half* d1 = s3 + 16 * V4 * np; __half* d2 = d1 + 304 * V4 * np; __half* s4 = d2 + 304 * V4 * np;
     const ConvUnit* U = net.units;
-    static const bool fuse_side = getenv("SN_TC_FUSE_SIDE") ? atoi(getenv("SN_TC_FUSE_SIDE")) != 0 : true;
+    // side_op1 / side_op2 can ride in the epilogue of conv1_3 / conv2_3 (SIDE kernel variant).  Measured on B200 (40 pair-cubes
+    // of 64^3, exact): conv1_3 2.13 -> 3.12 ms for a saved 0.85 ms side_op1 launch, i.e. the 512 extra FMAs per voxel make the
+    // 128-thread epilogue the bottleneck of a 2-channel-block main loop.  Off by default; SN_TC_FUSE_SIDE=1 enables it.
+    static const bool fuse_side = getenv("SN_TC_FUSE_SIDE") ? atoi(getenv("SN_TC_FUSE_SIDE")) != 0 : false;
     int rc;
 #define RUN(x) do { rc = (x); if (rc != SN_OK) return rc; } while (0)
 #define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))

@@ -494,3 +494,28 @@ def test_reconstruct_cubes_batching_and_npz(torch_cuda, params, cams, tmp_path):
     assert all(np.array_equal(x, y) for x, y in zip(back[0], res[0])) and np.array_equal(back[5]["xyz"], res[5]["xyz"])
     assert len(masks) == len(res[0]) and masks[0].dtype == bool
     assert reconstruct.reconstruct_cubes(hot, cubes[:0], pairs[:0], w[:0], D, Dc) == "Empty!"
+
+
+def test_forward_with_fused_side_epilogue_subprocess(torch_cuda):
+    """SN_TC_FUSE_SIDE=1 (side_op1 / side_op2 evaluated in the epilogue of conv1_3 / conv2_3; read once per process, hence the
+    subprocess): same <= 1e-4 bound against the oracle."""
+    import os, subprocess, sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from tests import util\n"
+        "from tests.test_gpu_parity import _real_like_X\n"
+        "from oracle import surfacenet_oracle as so\n"
+        "from surfacenet_b200 import SurfaceNet, weights\n"
+        "params = weights.synthetic_params(0)\n"
+        "X, *_ = _real_like_X(util.dtu_cameras(), 32, n_cubes=1, n_vp=2, seed=3)\n"
+        "w = np.array([[0.4, 0.6]], np.float32)\n"
+        "fo, uo = so.nViewPair_SurfaceNet_fn(X, params, w, N_vp=2)\n"
+        "_, fn = SurfaceNet.SurfaceNet_inference(2, params, mode='exact')\n"
+        "f, u = fn(X, w)\n"
+        "print('ERR', float(np.abs(f - fo).max()), float(np.abs(u - uo).max()))\n" % util.REPO)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SN_TC_FUSE_SIDE="1"), stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    e = [float(x) for x in out.stdout.strip().splitlines()[-1].split()[1:]]
+    assert max(e) <= PROB_TOL, e

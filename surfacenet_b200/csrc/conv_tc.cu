@@ -550,6 +550,8 @@ __global__ void pool_blk_kernel(const __half* __restrict__ in, int cg, int P, in
 // out[o] = sum_t W[t] * stuffed[o + t - K/2], stuffed[p] = in[p/F] when p % F == 0 in all three dims: per dimension only
 // the taps t = t0, t0+F, ... with t0 = (K/2 - o) mod F are non-zero (<= ceil(K/F) of them).
 // grid = (ceil(So^2 / 256), So, n * cg_in): one thread per output voxel of one 8-channel group; HBM-write bound.
+constexpr int UP_PLANES = 4;           // output d-planes per thread: amortises the block prologue (tap table in smem)
+
 template <int F, int K>
 __global__ void __launch_bounds__(256)
 upsample_blk_kernel(const __half* __restrict__ in, const float* __restrict__ W, int cg_in, int P, int S,
@@ -561,37 +563,44 @@ upsample_blk_kernel(const __half* __restrict__ in, const float* __restrict__ W, 
     const int So = S * F;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= So * So) return;
-    const int oh = idx / So, ow = idx - oh * So, od = blockIdx.y;
-    const int g = blockIdx.z % cg_in;
-    const long long n = blockIdx.z / cg_in;
+    const int oh = idx / So, ow = idx - oh * So;
+    const long long n = blockIdx.z;
     const long long vol = (long long)S * S * S, volo = (long long)So * So * So;
-    const __half* base = in + ((n * P) * cg_in + g) * vol * 8;
+    for (int od = blockIdx.y * UP_PLANES; od < min(So, (int)(blockIdx.y + 1) * UP_PLANES); ++od) {
+    // the (<= NT^3) contributing low-resolution voxels and their taps: computed once, shared by all channel groups
+    int src[NT * NT * NT];
+    float wt[NT * NT * NT];
     const int td0 = (C0 - od) & (F - 1), th0 = (C0 - oh) & (F - 1), tw0 = (C0 - ow) & (F - 1);
-    float acc[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int jd = 0; jd < NT; ++jd)
 #pragma unroll
-    for (int jd = 0; jd < NT; ++jd) {
-        const int td = td0 + jd * F, pd = od + td - C0;
-        if (td >= K || pd < 0 || pd >= So) continue;
-#pragma unroll
-        for (int jh = 0; jh < NT; ++jh) {
-            const int th = th0 + jh * F, ph = oh + th - C0;
-            if (th >= K || ph < 0 || ph >= So) continue;
+        for (int jh = 0; jh < NT; ++jh)
 #pragma unroll
             for (int jw = 0; jw < NT; ++jw) {
-                const int tw = tw0 + jw * F, pw = ow + tw - C0;
-                if (tw >= K || pw < 0 || pw >= So) continue;
-                const float wt = sW[(td * K + th) * K + tw];
-                float v[8];
-                load_blk8(base + (((long long)(pd / F) * S + ph / F) * S + pw / F) * 8, (long long)cg_in * vol * 8, P, v);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q] = fmaf(wt, v[q], acc[q]);
+                const int td = td0 + jd * F, th = th0 + jh * F, tw = tw0 + jw * F;
+                const int pd = od + td - C0, ph = oh + th - C0, pw = ow + tw - C0;
+                const bool ok = td < K && th < K && tw < K && pd >= 0 && pd < So && ph >= 0 && ph < So && pw >= 0 && pw < So;
+                const int e = (jd * NT + jh) * NT + jw;
+                src[e] = ok ? ((pd / F) * S + ph / F) * S + pw / F : -1;
+                wt[e] = ok ? sW[(td * K + th) * K + tw] : 0.f;
             }
+    const long long o = ((long long)od * So + oh) * So + ow;
+    for (int g = 0; g < cg_in; ++g) {
+        const __half* base = in + ((n * P) * cg_in + g) * vol * 8;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int e = 0; e < NT * NT * NT; ++e) {
+            if (src[e] < 0) continue;
+            float v[8];
+            load_blk8(base + (long long)src[e] * 8, (long long)cg_in * vol * 8, P, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = fmaf(wt[e], v[q], acc[q]);
         }
+        store_blk8(out + ((n * P) * cg_total + cg_off + g) * volo * 8 + o * 8, (long long)cg_total * volo * 8, P, acc);
     }
-    store_blk8(out + ((n * P) * cg_total + cg_off + g) * volo * 8 + (((long long)od * So + oh) * So + ow) * 8,
-               (long long)cg_total * volo * 8, P, acc);
+    }
 }
 
 static inline int ew_blocks(long long total) { return (int)std::min<long long>(cdiv(total, 256), 148 * 16); }
@@ -945,8 +954,8 @@ static int upsample_blk_launch(const __half* in, const float* W, int k, int f, i
     const int So = S * f, cg_in = Cpad / 8;
     if (!n || !S) return SN_OK;
     SN_CHECK_ARG((k == 3 && f == 2) || (k == 5 && f == 4), "upsample: only (k=3, x2) and (k=5, x4) exist in SurfaceNet (nets/layers.py:383)");
-    SN_CHECK_ARG(So <= 65535 && (long long)n * cg_in <= 65535, "upsample: grid too large");
-    dim3 grid((unsigned)cdiv((long long)So * So, 256), (unsigned)So, (unsigned)(n * cg_in));
+    SN_CHECK_ARG(So <= 65535 && n <= 65535, "upsample: grid too large");
+    dim3 grid((unsigned)cdiv((long long)So * So, 256), (unsigned)cdiv(So, UP_PLANES), (unsigned)n);
     if (f == 2) upsample_blk_kernel<2, 3><<<grid, 256, 0, st>>>(in, W, cg_in, P, S, out, cg_total, cg_off);
     else upsample_blk_kernel<4, 5><<<grid, 256, 0, st>>>(in, W, cg_in, P, S, out, cg_total, cg_off);
     SN_LAUNCHED();

@@ -625,6 +625,8 @@ struct TcState {
     TcUnit units[kNumUnits];
     float* w3 = nullptr; float scale3 = 0.f, shift3 = 0.f;
     PFN_cuTensorMapEncodeTiled encode = nullptr;
+    cudaStream_t side_stream = nullptr;            // the side-output branch (side convs + up-samplers) runs beside the main chain
+    cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::map<int, std::pair<TileCfg, long long>> tuned;     // (unit, mode, S) -> best tile configuration, work it was measured at
 };
 
@@ -728,6 +730,8 @@ void tc_destroy(Net& net) {
         cudaFree(st->units[u].side_w);
     }
     cudaFree(st->w3);
+    if (st->side_stream) cudaStreamDestroy(st->side_stream);
+    for (cudaEvent_t e : st->side_ev) if (e) cudaEventDestroy(e);
     delete st;
     net.tc = nullptr;
 }
@@ -991,33 +995,55 @@ static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float*
     // of 64^3, exact): conv1_3 2.13 -> 3.12 ms for a saved 0.85 ms side_op1 launch, i.e. the 512 extra FMAs per voxel make the
     // 128-thread epilogue the bottleneck of a 2-channel-block main loop.  Off by default; SN_TC_FUSE_SIDE=1 enables it.
     static const bool fuse_side = getenv("SN_TC_FUSE_SIDE") ? atoi(getenv("SN_TC_FUSE_SIDE")) != 0 : false;
+    // The side-output branch (side_op* 1x1x1 convs and the fixed-tap up-samplers that fill the 64-channel concat tensor) only
+    // joins the main chain at merge_conv.  It is HBM-bound while the main chain is tensor-bound, so it runs on a second stream
+    // (fork after conv1_3 / conv2_3 / conv3_3 / conv4_3, join before merge_conv) and can hide under conv2_1 ... conv4_3.
+    // Measured on B200 (C3, exact): 87.35 ms/step without, 87.14 ms with -- the step runs at the 1 kW power cap (SM clock
+    // 1.6-1.7 GHz), so overlapping the memory-bound branch only lowers the clock.  Off by default; SN_TC_SIDE_STREAM=1 enables it.
+    static const bool side_stream_on = getenv("SN_TC_SIDE_STREAM") ? atoi(getenv("SN_TC_SIDE_STREAM")) != 0 : false;
+    TcState* ts = (TcState*)net.tc;
+    cudaStream_t sb = st;
+    if (side_stream_on) {
+        if (!ts->side_stream) {
+            SN_CUDA(cudaStreamCreateWithFlags(&ts->side_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t& e : ts->side_ev) SN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        sb = ts->side_stream;
+    }
     int rc;
 #define RUN(x) do { rc = (x); if (rc != SN_OK) return rc; } while (0)
 #define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))
+#define SIDECONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, sb))
+#define FORK(i) do { if (sb != st) { SN_CUDA(cudaEventRecord(ts->side_ev[i], st)); SN_CUDA(cudaStreamWaitEvent(sb, ts->side_ev[i], 0)); } } while (0)
     RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
     CONV(U_CONV1_1, x0, S1, a1, 4, 0);
     CONV(U_CONV1_2, a1, S1, a2, 4, 0);
     if (fuse_side) RUN(conv_tc_launch(net, U_CONV1_3, a2, n, S1, P, EPI_BLK, a1, 4, 0, nullptr, st, U_SIDE1, cat, 8, 0));   // + side_op1 -> concat[0:16]
-    else { CONV(U_CONV1_3, a2, S1, a1, 4, 0); CONV(U_SIDE1, a1, S1, cat, 8, 0); }
+    else { CONV(U_CONV1_3, a2, S1, a1, 4, 0); FORK(0); SIDECONV(U_SIDE1, a1, S1, cat, 8, 0); }
     RUN(pool_launch(a1, n, 32, P, S1, p1, st));
     CONV(U_CONV2_1, p1, S2, b1, 10, 0);
     CONV(U_CONV2_2, b1, S2, b2, 10, 0);
-    if (fuse_side) RUN(conv_tc_launch(net, U_CONV2_3, b2, n, S2, P, EPI_BLK, b1, 10, 0, nullptr, st, U_SIDE2, s2, 2, 0));    // + side_op2
-    else { CONV(U_CONV2_3, b2, S2, b1, 10, 0); CONV(U_SIDE2, b1, S2, s2, 2, 0); }
-    RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, st));   // -> concat[16:32]
+    if (fuse_side) { RUN(conv_tc_launch(net, U_CONV2_3, b2, n, S2, P, EPI_BLK, b1, 10, 0, nullptr, st, U_SIDE2, s2, 2, 0)); FORK(1); }   // + side_op2
+    else { CONV(U_CONV2_3, b2, S2, b1, 10, 0); FORK(1); SIDECONV(U_SIDE2, b1, S2, s2, 2, 0); }
+    RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, sb));   // -> concat[16:32]
     RUN(pool_launch(b1, n, 80, P, S2, p2, st));
     CONV(U_CONV3_1, p2, S4, c1, 20, 0);
     CONV(U_CONV3_2, c1, S4, c2, 20, 0);
     CONV(U_CONV3_3, c2, S4, c1, 20, 0);
-    CONV(U_SIDE3, c1, S4, s3, 2, 0);
-    RUN(upsample_blk_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, P, S4, cat, 8, 4, st));   // -> concat[32:48]
+    FORK(2);
+    SIDECONV(U_SIDE3, c1, S4, s3, 2, 0);
+    RUN(upsample_blk_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, P, S4, cat, 8, 4, sb));   // -> concat[32:48]
     CONV(U_CONV4_1, c1, S4, d1, 38, 0);
     CONV(U_CONV4_2, d1, S4, d2, 38, 0);
     CONV(U_CONV4_3, d2, S4, d1, 38, 0);
-    CONV(U_SIDE4, d1, S4, s4, 2, 0);
-    RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, st));   // -> concat[48:64]
+    FORK(3);
+    SIDECONV(U_SIDE4, d1, S4, s4, 2, 0);
+    RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, sb));   // -> concat[48:64]
+    if (sb != st) { SN_CUDA(cudaEventRecord(ts->side_ev[4], sb)); SN_CUDA(cudaStreamWaitEvent(st, ts->side_ev[4], 0)); }   // join
     CONV(U_MERGE1, cat, S1, m1, 14, 0);
     RUN(conv_tc_launch(net, U_MERGE2, m1, n, S1, P, EPI_FINAL, nullptr, 0, 0, prob_out, st));   // + merge_conv3 + sigmoid
+#undef FORK
+#undef SIDECONV
 #undef CONV
 #undef RUN
     return SN_OK;

@@ -35,7 +35,7 @@ extern "C" {
 #define SN_ERR_NOMEM    (-4)   /* workspace too small                        -> RuntimeError */
 
 #define SN_MODE_FP32     0     /* CUDA-core fp32 convolutions (exact reference precision)        */
-#define SN_MODE_TC_EXACT 1     /* tcgen05, fp16 hi+lo split operands, 3 MMAs / product           */
+#define SN_MODE_TC_EXACT 1     /* tcgen05, fp16 hi+lo split of both operands (3 products, 2 MMAs): <= 1e-4 */
 #define SN_MODE_TC_FAST  2     /* tcgen05, single-pass fp16 operands (does NOT meet 1e-4 parity) */
 
 #define SN_ACT_RELU      0

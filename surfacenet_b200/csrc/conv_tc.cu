@@ -1073,7 +1073,11 @@ int tc_layer_conv(const Net& net, int u, const float* in, int n, int S, float* o
     const long long vol = (long long)S * S * S;
     __half *bi = nullptr, *bo = nullptr;
     SN_CUDA(cudaMallocAsync((void**)&bi, (size_t)n * P * tu.Cin_pad * vol * 2 + 1024, st));
-    SN_CUDA(cudaMallocAsync((void**)&bo, (size_t)n * P * tu.Cout_pad * vol * 2 + 1024, st));
+    if (cudaMallocAsync((void**)&bo, (size_t)n * P * tu.Cout_pad * vol * 2 + 1024, st) != cudaSuccess) {
+        cudaFreeAsync(bi, st);
+        set_error("tensor-core layer call: out of device memory");
+        return SN_ERR_CUDA;
+    }
     int rc = pack_launch(in, n, cu.Cin, tu.Cin_pad, P, vol, bi, st);
     if (rc == SN_OK) rc = conv_tc_launch(net, u, bi, n, S, P, EPI_BLK, bo, tu.Cout_pad / 8, 0, nullptr, st);
     if (rc == SN_OK) rc = unpack_launch(bo, n, cu.Cout, tu.Cout_pad, P, vol, out, st);

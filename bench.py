@@ -113,7 +113,7 @@ def make_images(n_views=49, H=1200, W=1600):
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_step(wl, params, cams, imgs, sample_cubes, threads):
+def cpu_reference_step(wl, params, cams, imgs, sample_cubes, threads, return_outputs=False):
     """The reference path on the host: numpy CVC + mean (utils/CVC.py), torch-CPU fp32 network + fusion
     (nets/SurfaceNet.py restated), float16 cast + numpy ray pooling (utils/sparseCubes.py:115,57-62).
     Returns seconds for `sample_cubes` cubes x n_vp pairs."""
@@ -127,8 +127,11 @@ def cpu_reference_step(wl, params, cams, imgs, sample_cubes, threads):
     X = cvc_oracle.gen_coloredCubes(pairs.astype(np.int64), xyz, resol, cams, imgs, wl["D"])
     _, X = cvc_oracle.preprocess_augmentation(None, X, util.MEAN6[None, :, None, None, None], False, False)
     fused, _ = surfacenet_oracle.nViewPair_SurfaceNet_fn(X, params, w, N_vp=wl["n_vp"], chunk=1)
-    raypool_oracle.votes_batch(fused, pairs, xyz, resol, cams, 0.46)
-    return time.perf_counter() - t0
+    votes = raypool_oracle.votes_batch(fused, pairs, xyz, resol, cams, 0.46)
+    dt = time.perf_counter() - t0
+    if return_outputs:
+        return dt, dict(pairs=pairs, xyz=xyz, resol=resol, w=w, fused=fused, votes=votes)
+    return dt
 
 
 def run_reference(args, wl):
@@ -317,9 +320,14 @@ def run_gpu(args, wl):
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_reference_step(dict(wl, D=16), params, cams, imgs, 1, threads)        # warm torch's thread pool
-            dt = cpu_reference_step(wl, params, cams, imgs, 1, threads)
+            dt, ref = cpu_reference_step(wl, params, cams, imgs, 1, threads, return_outputs=True)
             line["cpu_baseline"] = {"value": V / dt, "unit": "voxels/s", "cores": threads, "kind": "port",
                                     "sample": "1 cube x %d view-pairs of %d^3 (%.1f s): numpy CVC + torch-CPU fp32 net + numpy ray pooling" % (n_vp, D, dt)}
+            # the CPU leg doubles as the checker: the same cube through the timed GPU entry, compared with what the port computed
+            got = hp.infer_batch_host(ref["pairs"], ref["xyz"], ref["resol"], ref["w"], D)
+            line["parity_check"] = {"case": "the cpu_baseline cube (1 cube x %d view-pairs of %d^3), mode %s" % (n_vp, D, mode),
+                                    "max_abs_prob_vs_port": float(np.abs(got["fused"] - ref["fused"]).max()), "tolerance": 1e-4,
+                                    "votes_differing_voxels": int((got["votes"] != ref["votes"]).sum()), "voxels": int(V)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

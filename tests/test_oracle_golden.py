@@ -114,3 +114,98 @@ def test_dense2sparse_oracle_matches_reference_outputs(golden, cams, name):
                                                  rayPool_thresh=0, enable_centerCrop=True, cube_Dcenter=case["Dcenter"],
                                                  enable_rayPooling=True, cameraPOs=cams, cameraTs=None)
     _check_sparse(res, golden, name)
+
+
+# ---- "next" row N4: utils/denoising.py, utils/adapthresh.py -------------------------------------------------------------
+from oracle import postprocess_oracle as post
+
+
+@pytest.fixture(scope="module")
+def post_golden():
+    import os
+    return np.load(os.path.join(util.REPO, "tests", "golden", "postprocess_golden.npz"))
+
+
+def _doc_cluster_inputs():
+    ijk = [np.array([[1, 0, 0], [2, 2, 2], [3, 3, 3], [1, 0, 1], [2, 3, 3], [0, 3, 3], [1, 2, 2]]),
+           np.array([[0, 2, 3], [0, 1, 0], [0, 0, 0], [0, 3, 3]]), np.array([[0, 2, 3], [0, 1, 0], [0, 2, 3]]),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3], [3, 3, 3]], dtype=np.uint8)]
+    mask = [np.array([1, 0, 1, 1, 1, 1, 1], dtype=bool), np.array([1, 1, 0, 1], dtype=bool), np.array([0, 0, 0], dtype=bool),
+            np.array([1, 1, 1, 1, 1], dtype=bool)]
+    return ijk, mask
+
+
+def test_cluster_inCube_reference_doctest_known_answers(post_golden):
+    # utils/denoising.py:26-38
+    ijk, mask = _doc_cluster_inputs()
+    lab, n = post.cluster_inCube(ijk, mask)
+    assert [l.tolist() for l in lab] == [[2, 0, 4, 2, 4, 1, 3], [2, 1, 0, 2], [0, 0, 0], [2, 2, 1, 2, 3]] and n == [4, 2, 0, 3]
+    lab, n = post.cluster_inCube(ijk, mask, neighbor_dist=3)
+    assert [l.tolist() for l in lab] == [[2, 0, 1, 2, 1, 1, 1], [2, 1, 0, 2], [0, 0, 0], [2, 2, 1, 2, 3]] and n == [2, 2, 0, 3]
+    for nd in (1, 2, 3):
+        lab, n = post.cluster_inCube(ijk, mask, neighbor_dist=nd)
+        assert np.array_equal(np.concatenate(lab).astype(np.int64), post_golden["doc_cluster_nd%d_labels" % nd])
+        assert np.array_equal(np.asarray(n), post_golden["doc_cluster_nd%d_n" % nd])
+
+
+def test_mark_overlappingLabels_reference_doctest_known_answers():
+    # utils/denoising.py:82-94
+    cube_ijk = np.array([[1, 6, 8], [2, 6, 8], [2, 7, 8], [2, 5, 8]], dtype=np.uint8)
+    ijk = [np.array([[1, 0, 0], [2, 2, 2], [3, 2, 3], [3, 3, 3], [1, 0, 1], [2, 3, 3], [3, 0, 3]], dtype=np.uint8),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3], [1, 0, 3], [3, 3, 0]], dtype=np.uint8),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3]], dtype=np.uint8),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3], [3, 3, 3]], dtype=np.uint8)]
+    mask = [np.array([1, 0, 0, 1, 1, 1, 1], dtype=bool), np.array([1, 1, 0, 1, 1, 1], dtype=bool), np.array([0, 0, 0, 0], dtype=bool),
+            np.array([1, 1, 1, 1, 1], dtype=bool)]
+    ovl, lab = post.mark_overlappingLabels(cube_ijk, ijk, mask, D_cube=4)
+    assert ovl == [[2, 3], [1, 2], [], [2]]
+    assert [l.tolist() for l in lab] == [[1, 0, 0, 2, 1, 2, 3], [1, 1, 0, 1, 2, 3], [0, 0, 0, 0], [2, 2, 1, 2, 3]]
+
+
+def test_denoise_crossCubes_reference_doctest_known_answers():
+    # utils/denoising.py:160-172
+    cube_ijk = np.array([[1, 6, 8], [2, 6, 8], [2, 7, 8], [2, 5, 8]], dtype=np.uint8)
+    ijk = [np.array([[1, 0, 0], [2, 2, 2], [3, 3, 3], [1, 0, 1], [2, 3, 3]], dtype=np.uint8),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3], [3, 3, 0]], dtype=np.uint8),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3]], dtype=np.uint8),
+           np.array([[0, 2, 3], [0, 1, 3], [0, 0, 0], [0, 3, 3], [3, 3, 3]], dtype=np.uint8)]
+    mask = [np.array([1, 0, 1, 1, 1], dtype=bool), np.array([1, 1, 0, 1, 1], dtype=bool), np.array([0, 0, 0, 0], dtype=bool),
+            np.array([1, 1, 1, 1, 1], dtype=bool)]
+    keep = post.denoise_crossCubes(cube_ijk, ijk, mask, D_cube=4)
+    assert [k.tolist() for k in keep] == [[False, False, True, False, True], [True, True, False, True, False],
+                                          [False, False, False, False], [True, True, False, True, False]]
+
+
+def test_adapthresh_helpers_reference_doctest_known_answers():
+    # utils/adapthresh.py:33-41
+    Occ = np.array([[1, 5, 2], [5, 2, 0], [0, 1, 5], [2, 1, 1], [4, 5, 5]])
+    gt = Occ[2:3] - np.array([[0, 0, 3]])
+    res = post.access_partial_Occupancy_ijk(Occ.copy(), (-1, 0, 1), D_cube=6)
+    assert gt.shape == res.shape and np.array_equal(gt, res)
+    assert np.array_equal(Occ[1:4, :2], post.access_partial_Occupancy_ijk(Occ[:, :2].copy(), (0, -1), D_cube=6))
+    # utils/adapthresh.py:73-76
+    ijk1 = np.array([[1, 0], [2, 3], [222, 666], [0, 0]])
+    ijk2 = np.array([[11, 10], [2, 3], [22, 66], [0, 0], [7, 17]])
+    assert post.sparseOccupancy_AND_XOR(ijk1, ijk2) == (2, 5)
+
+
+@pytest.mark.parametrize("name", ["g322_d12", "g233_d16_shuffled", "g222_d13_odd_dup", "g141_d10_thin"])
+def test_postprocess_oracle_matches_reference_outputs(post_golden, name):
+    case = util.post_cases()[name]
+    sc = case["scene"]
+    g = lambda k: post_golden["post_%s_%s" % (name, k)]
+    cat = lambda lst: np.concatenate([np.asarray(x) for x in lst])
+    mask0 = post.filter_voxels([], sc["pred_list"], 0.7, sc["votes_list"], case["rp"])
+    assert np.array_equal(cat(mask0).astype(np.uint8), g("mask_tau"))
+    for nd in (1, 3):
+        ovl, lab = post.mark_overlappingLabels(sc["cube_ijk"], sc["ijk_list"], mask0, sc["D"], neighbor_dist=nd)
+        assert np.array_equal(cat(lab).astype(np.int64), g("labels_nd%d" % nd))
+        assert np.array_equal(cat([np.isin(l, o) for l, o in zip(lab, ovl)]).astype(np.uint8), g("ovl_nd%d" % nd))
+    keep = post.denoise_crossCubes(sc["cube_ijk"], sc["ijk_list"], mask0, sc["D"])
+    assert np.array_equal(cat(keep).astype(np.uint8), g("denoised_tau"))
+    res = post.adapthresh_core(sc["pred_list"], sc["ijk_list"], sc["votes_list"], sc["cube_ijk"], case["iters"], sc["D"], case["init"],
+                               case["init"], case["maxp"], case["rp"], case["beta"])
+    assert np.array_equal(cat(res["init_denoised"]).astype(np.uint8), g("ada_init_denoised"))
+    for i, it in enumerate(res["iters"]):
+        assert np.array_equal(it["probThresh"], g("ada_thresh")[i])
+        assert np.array_equal(cat(it["denoised"]).astype(np.uint8), g("ada_denoised")[i])

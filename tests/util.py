@@ -109,3 +109,63 @@ def sparse_cases(cams):
     c["d32"] = dict(batch(32, 2, 3), Dcenter=26)                   # params.py:107 __cube_Dcenter[32] = 26
     c["all_empty"] = dict(batch(8, 2, 1, empty=(0, 1)), Dcenter=6)
     return c
+
+
+# ---- "next" row N4: sparse scenes for denoising.denoise_crossCubes / adapthresh.adapthresh ------------------------------
+def sparse_scene(grid, D, seed=0, noise=0.15, floaters=6, min_prob=0.46, shuffle=False, empty=(), dup_last=False, thick=0.09,
+                 max_votes=10, gain_spread=0.35):
+    """A wavy sheet cut by a grid of half-overlapping cubes (cube (i,j,k) starts at voxel (i,j,k)*D/2 of a global grid), as
+    main_reconstruct.py leaves it after append_dense_2sparseList: per-cube voxel lists (np.where order unless `shuffle`),
+    float16 predictions (each cube sees its own noise, as overlapping CNN windows do), uint8 ray-pool votes, plus a few
+    isolated floaters per cube (the noise denoise_crossCubes removes).
+    -> dict(cube_ijk (C,3) uint32, ijk_list, pred_list, votes_list, rgb_list, param (C,) PARAM_DTYPE)"""
+    rs = np.random.RandomState(seed)
+    h = D // 2
+    gi, gj, gk = grid
+    ext = np.array([(gi + 1) * h, (gj + 1) * h, (gk + 1) * h], np.float64)
+    cube_ijk, ijk_l, pred_l, votes_l, rgb_l = [], [], [], [], []
+    g = np.arange(D)
+    for ci in range(gi):
+        for cj in range(gj):
+            for ck in range(gk):
+                n = len(cube_ijk)
+                X, Y, Z = np.meshgrid(ci * h + g, cj * h + g, ck * h + g, indexing="ij")
+                x, y, z = X / ext[0], Y / ext[1], Z / ext[2]
+                d = z - (0.5 + 0.22 * np.sin(5.0 * x + seed) * np.cos(4.0 * y))
+                sig = thick * (1.0 + gain_spread * (2 * rs.rand() - 1))            # each cube sees a slightly thicker / thinner sheet
+                p = np.exp(-d * d / (2 * sig * sig)) * (1.0 - noise * rs.rand(D, D, D))
+                fl = rs.randint(0, D, size=(floaters, 3))
+                p[fl[:, 0], fl[:, 1], fl[:, 2]] = 0.6 + 0.39 * rs.rand(floaters)
+                if n in empty:
+                    p[:] = 0.1
+                p16 = p.astype(np.float16)
+                sel = np.where(p16 > np.float16(min_prob))
+                ijk = np.c_[sel].astype(np.uint8)
+                pr = p16[sel]
+                votes = np.clip(np.round(pr.astype(np.float64) * max_votes + rs.randint(-2, 3, size=pr.shape)), 0, max_votes).astype(np.uint8)
+                rgb = rs.randint(0, 256, size=(ijk.shape[0], 3)).astype(np.uint8)
+                if shuffle:
+                    o = rs.permutation(ijk.shape[0])
+                    ijk, pr, votes, rgb = ijk[o], pr[o], votes[o], rgb[o]
+                cube_ijk.append((ci, cj, ck)); ijk_l.append(ijk); pred_l.append(pr); votes_l.append(votes); rgb_l.append(rgb)
+    if dup_last:                                             # a repeated cube index: the reference's dict keeps the later one
+        cube_ijk.append(cube_ijk[0]); ijk_l.append(ijk_l[1].copy()); pred_l.append(pred_l[1].copy())
+        votes_l.append(votes_l[1].copy()); rgb_l.append(rgb_l[1].copy())
+    C = len(cube_ijk)
+    param = np.zeros(C, PARAM_DTYPE)
+    param["ijk"] = np.asarray(cube_ijk, np.uint32)
+    param["resol"] = np.float32(0.4)
+    param["xyz"] = (np.asarray(cube_ijk, np.float64) * h * 0.4 + np.array([-30.0, 10.0, 600.0])).astype(np.float32)
+    return dict(cube_ijk=np.asarray(cube_ijk, np.uint32), ijk_list=ijk_l, pred_list=pred_l, votes_list=votes_l, rgb_list=rgb_l,
+                param=param, D=D)
+
+
+def post_cases():
+    """Small scenes (every per-half-cube count stays <= 2048, see oracle/postprocess_oracle.py) for the golden vectors."""
+    c = {}
+    c["g322_d12"] = dict(scene=sparse_scene((3, 2, 2), 12, seed=1), init=0.5, maxp=0.9, rp=3, beta=6, iters=4)
+    c["g233_d16_shuffled"] = dict(scene=sparse_scene((2, 3, 3), 16, seed=2, shuffle=True, empty=(4,), thick=0.06), init=0.5, maxp=0.9, rp=2,
+                                  beta=6, iters=5)
+    c["g222_d13_odd_dup"] = dict(scene=sparse_scene((2, 2, 2), 13, seed=3, dup_last=True), init=0.6, maxp=0.8, rp=0, beta=3, iters=3)
+    c["g141_d10_thin"] = dict(scene=sparse_scene((1, 4, 1), 10, seed=4, thick=0.04, floaters=12), init=0.5, maxp=0.9, rp=4, beta=6, iters=3)
+    return c

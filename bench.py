@@ -4,6 +4,7 @@ view-pair fusion -> float16 -> ray-pool votes) on N B200s of one node.
 
     python bench.py [--gpus N --steps K --warmup W] [--workload c3|c2|c4] [--mode fp32|exact|fast]
     python bench.py --impl reference ...      the CPU restatement of the reference path on the host cores
+    python bench.py --workload post ...       "next" row N4: filter + denoise + adapthresh on the scene's sparse cubes
 
 A "step" = one batch of the hot loop of main_reconstruct.py:132-162 per GPU.  Workload (default c3,
 BASELINE.json configs[2], the 64^3 configuration the headline target is quoted on; largest single-GPU
@@ -334,17 +335,181 @@ def run_gpu(args, wl):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# "next" row N4: the post-processing of the scene's sparse cubes (main_reconstruct.py:170-173 + utils/adapthresh.py:91-178)
+POST_GRID, POST_D, POST_ITERS = (8, 8, 4), 52, 8          # 256 half-overlapping 52^3 centre cubes, params.py:107,113
+
+
+def post_step_oracle(sc, iters):
+    """The reference's CPU post-processing (py3 restatement): fixed-threshold filter + denoise, then `iters` refinement
+    iterations each followed by a denoise."""
+    from oracle import postprocess_oracle as post
+    D = sc["D"]
+    m = post.filter_voxels([], sc["pred_list"], 0.7, sc["votes_list"], 8)
+    post.denoise_crossCubes(sc["cube_ijk"], sc["ijk_list"], m, D)
+    post.adapthresh_core(sc["pred_list"], sc["ijk_list"], sc["votes_list"], sc["cube_ijk"], iters, D, 0.5, 0.5, 0.9, 8, 6)
+
+
+def run_post(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    from tests import util
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sc = util.sparse_scene((2, 2, 2), POST_D, seed=50, floaters=40, thick=0.05)
+        n = sum(x.shape[0] for x in sc["ijk_list"])
+        for _ in range(min(args.warmup, 1)):
+            post_step_oracle(sc, 1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            post_step_oracle(sc, POST_ITERS)
+        dt = (time.perf_counter() - t0) / args.steps
+        desc = "8 cubes of %d^3 (%d voxels), %d refinement iterations per step: numpy/scipy restatement, 1 thread" % (POST_D, n, POST_ITERS)
+        print(json.dumps({"impl": "reference", "metric": "sparse voxels/sec through post-processing (filter + denoise + adapthresh)",
+                          "value": n / dt, "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f16",
+                          "data": "synthetic", "config": {"workload": "post", "sample": desc},
+                          "cpu_baseline": {"value": n / dt, "unit": "voxels/s", "cores": 1, "kind": "port", "sample": desc},
+                          "e2e": {"value": n / dt, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    import torch
+    import torch.distributed as dist
+    from surfacenet_b200 import _lib, adapthresh
+    from surfacenet_b200.sparse_device import DeviceSparseCubes
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    # every rank post-processes its own slab of the scene (replicas of the same synthetic generator with another seed)
+    sc = util.sparse_scene(POST_GRID, POST_D, seed=60 + rank, floaters=40, thick=0.05)
+    dsc = DeviceSparseCubes(sc["cube_ijk"], sc["ijk_list"], sc["pred_list"], sc["votes_list"])
+    N, C = dsc.N, dsc.C
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    parts = {"filter": 0.0, "denoise": 0.0, "adapthresh_iter": 0.0}
+    n_calls = {"filter": 0, "denoise": 0, "adapthresh_iter": 0}
+
+    def timed_call(name, fn, record):
+        if not record:
+            return fn()
+        a, b = ev(), ev()
+        a.record(); r = fn(); b.record()
+        pending.append((name, a, b))
+        return r
+
+    pending = []
+
+    def step_device(record=False):
+        m = timed_call("filter", lambda: dsc.filter_voxels(None, prob_thresh=0.7, rayPool_thresh=8), record)
+        timed_call("denoise", lambda: dsc.denoise(m, POST_D), record)                       # main_reconstruct.py:170-173
+        init = dsc.filter_voxels(None, prob_thresh=0.5, rayPool_thresh=8)                     # adapthresh.py:103
+        timed_call("denoise", lambda: dsc.denoise(init, POST_D), record)
+        mask = init.clone()
+        thresh = torch.full((C,), 0.5, dtype=torch.float64, device=dev)
+        for _ in range(POST_ITERS):
+            timed_call("adapthresh_iter", lambda: dsc.adapthresh(init, mask, thresh, POST_D, 0.9, 6, n_iter=1), record)
+            timed_call("denoise", lambda: dsc.denoise(mask, POST_D), record)
+        return thresh
+
+    def step_host():
+        return adapthresh.adapthresh_lists(sc["pred_list"], sc["ijk_list"], sc["votes_list"], sc["cube_ijk"], POST_ITERS, POST_D, 0.5, 0.9, 8, 6)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn(); flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.lib.sn_launch_count_reset()
+        evs = [(ev(), ev()) for _ in range(steps)]
+        t0 = time.time()
+        for a, b in evs:
+            a.record(); fn(); b.record(); flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, int(_lib.lib.sn_launch_count()) // steps, (t0, t1)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, launches, win = timed(lambda: step_device(False), args.steps, args.warmup)
+    clocks = sampler.window(*win) if sampler else None
+    step_device(True)                                         # per-call split, separate pass (events around each C-ABI call)
+    torch.cuda.synchronize()
+    for name, a, b in pending:
+        parts[name] += a.elapsed_time(b); n_calls[name] += 1
+    t0 = time.perf_counter()
+    e2e_steps = max(1, args.steps // 2)
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        _, hbm_peak, peak_src = peaks()
+        # algorithmic bytes per voxel and call (DESIGN.md section 7): every kernel streams each per-voxel array it needs once
+        #   denoise (10 launches): vox_cube 4 w | bitmap: ijk 3 + mask 1 + vox_cube 4 | init: vox_cube 4 + parent 4 w + ovl 1 w |
+        #     union: ijk 3 + mask 1 + vox_cube 4 | root: vox_cube 4 + parent 4 + root 4 w | overlap: ijk 3 + mask 1 + vox_cube 4 + root 4 |
+        #     keep: ijk 3 + mask 1 + vox_cube 4 + root 4 + ovl 1 + keep 1 w                              = 67 B per voxel
+        #   adapthresh iteration (9 launches): vox_cube 4 w + bitmap 8 | occ0: ijk 3 + pred 2 + mask 1 | count: same 6 |
+        #     filter: pred 2 + mask 1 + vox_cube 4 + mask 1 w                                             = 32 B per voxel
+        #   (the per-cube bitmaps / prefixes, 2 x 17.6 KB per cube, stay in L2 and are not counted)
+        bytes_call = {"denoise": 67.0 * N, "adapthresh_iter": 32.0 * N, "filter": 12.0 * N}
+        dom = max(("denoise", "adapthresh_iter"), key=lambda k: parts[k])
+        dom_ms = parts[dom] / max(n_calls[dom], 1)
+        achieved = bytes_call[dom] / (dom_ms * 1e-3) / 1e9
+        line = {"metric": "sparse voxels/sec through post-processing (filter + denoise + adapthresh)", "value": world * N / (ms_dev * 1e-3),
+                "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f16", "data": "synthetic",
+                "config": {"workload": "post: %dx%dx%d half-overlapping %d^3 centre cubes (%d cubes, %d sparse voxels) per GPU; step = filter(tau,gamma) + denoise + "
+                                       "adapthresh init + %d x (refinement iteration + denoise)" % (POST_GRID + (POST_D, C, N, POST_ITERS)),
+                           "l2": "256 MiB flush write between timed steps", "parallelism": "independent slabs x%d, no collective" % world},
+                "e2e": {"value": world * N / (ms_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(N * (3 + 2 + 1) + C * 20), "d2h_bytes_per_step": int(N * (POST_ITERS * 2 + 2) + C * 8),
+                        "what": "adapthresh_lists: per-cube numpy lists in, per-iteration masks + denoised masks out (wall clock)"},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "the %s C-ABI call (%d launches)" % (dom, {"denoise": 10, "adapthresh_iter": 9}[dom]),
+                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                             "peak_source": peak_src, "bytes_per_call": bytes_call[dom], "ms_per_call": dom_ms,
+                             "calls_ms_per_step": {k: parts[k] for k in parts}, "calls_per_step": n_calls}}
+        if world == 1 and not args.no_cpu_baseline:
+            small = util.sparse_scene((2, 2, 2), POST_D, seed=50, floaters=40, thick=0.05)
+            n_small = sum(x.shape[0] for x in small["ijk_list"])
+            t0 = time.perf_counter()
+            post_step_oracle(small, 2)
+            dt = (time.perf_counter() - t0) * (1 + 2 + 2 * POST_ITERS) / (1 + 2 + 2 * 2)          # scale the iteration count up to POST_ITERS
+            line["cpu_baseline"] = {"value": n_small / dt, "unit": "voxels/s", "cores": 1, "kind": "port",
+                                    "sample": "8 cubes of %d^3 (%d voxels), 2 of %d refinement iterations timed and scaled: numpy/scipy restatement of "
+                                              "denoising.py + adapthresh.py" % (POST_D, n_small, POST_ITERS)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["post"])
     ap.add_argument("--mode", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "post":
+        return run_post(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)

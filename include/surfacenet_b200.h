@@ -206,6 +206,47 @@ int sn_infer_batch_sparse(const sn_net* net, const uint8_t* images_dev, const in
                           uint8_t* ijk_out_dev, void* pred_out_dev, uint8_t* rgb_out_dev, uint8_t* votes_out_dev, int64_t capacity,
                           void* workspace_dev, int64_t workspace_bytes, int mode, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row N4: thresholding, cross-cube denoising and the adaptive-threshold refinement on the
+ * scene's sparse cubes, device resident.  Layout: ONE flat voxel array for the whole scene; cube n owns entries
+ * [cube_offset[n], cube_offset[n+1]) (the order of the reference's per-cube lists, i.e. of the NPZ arrays of
+ * utils/sparseCubes.py:330-366, whose cube_1st_vxlIndx_np is exactly cube_offset).
+ *   cube_ijk_dev (C,3) i32 cube grid index (param 'ijk');  cube_offset_dev (C+1) i64
+ *   ijk_dev (N,3) u8 voxel index inside the cube;  pred16_dev (N) f16;  votes_dev (N) u8;  masks (N) u8 (0/1)
+ *   grid_extent G: every masked voxel coordinate must be < G (<= 256); workspace: sn_sparse_post_workspace_bytes(C, N, G)
+ * sn_sparse_denoise and sn_sparse_adapthresh synchronise `stream` once at the end to read the error flags.
+ */
+int64_t sn_sparse_post_workspace_bytes(int n_cubes, int64_t n_vox, int grid_extent);
+
+/* utils/sparseCubes.py:205-243  filter_voxels: mask = [mask &] (pred >= prob_thresh) [& (votes >= rayPool_thresh)].
+ *   has_prob != 0: threshold = thresh_per_cube_dev[cube] (C doubles) or thresh_scalar when that pointer is NULL, rounded to
+ *   float16 for the comparison (numpy compares a float16 array with a python float in float16);
+ *   votes_dev != NULL and rayPool_thresh >= 0: votes >= rayPool_thresh;  and_into != 0: and with the incoming mask. */
+int sn_sparse_filter_voxels(const void* pred16_dev, const uint8_t* votes_dev, const int64_t* cube_offset_dev, int n_cubes,
+                            int64_t n_vox, const double* thresh_per_cube_dev, double thresh_scalar, int has_prob,
+                            int rayPool_thresh, int and_into, uint8_t* mask_inout_dev, void* workspace_dev,
+                            int64_t workspace_bytes, void* stream);
+
+/* utils/denoising.py:145-184  denoise_crossCubes(cube_ijk_np, vxl_ijk_list, vxl_mask_list, D_cube)  (neighbor_dist = 3) and its
+ * parts __cluster_inCube__ (8-62) / __mark_overlappingLabels__ (67-140) for neighbor_dist 1, 2, 3:
+ *   keep_out_dev (N) u8    = np.in1d(labels, overlappingLabels): masked voxels whose cluster shares a voxel with one of the
+ *                            26 neighbouring cubes (neighbour voxel + (D_cube/2)*shift == voxel), may be NULL
+ *   labels_out_dev (N) u32 = scipy.ndimage.label numbering (raster order of each cluster's first voxel), 0 = masked out; may be NULL
+ *   n_labels_out_dev (C) i32 clusters per cube; may be NULL */
+int sn_sparse_denoise(const int32_t* cube_ijk_dev, const int64_t* cube_offset_dev, const uint8_t* ijk_dev, const uint8_t* mask_dev,
+                      int n_cubes, int64_t n_vox, int grid_extent, int D_cube, int neighbor_dist, uint8_t* keep_out_dev,
+                      uint32_t* labels_out_dev, int32_t* n_labels_out_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* utils/adapthresh.py:126-174  n_iter iterations of the per-cube threshold refinement, no host round trip:
+ *   per dict cube (non-empty under init_mask_dev) and threshold perturbation [0.1, 0, -0.1]: cost = sum over the 6 face
+ *   neighbours of XOR(current half, neighbour half) - beta * AND (when both halves hold >= 6 voxels), accumulated in float16
+ *   as numpy 1.13 does; thresh += perturbation[argmin], clamped to max_probThresh; mask &= pred >= thresh.
+ *   thresh_inout_dev (C) f64, mask_inout_dev (N) u8 (start: init mask copy), argmin_out_dev (n_iter, C) i32 or NULL (-1 = not a dict cube) */
+int sn_sparse_adapthresh(const int32_t* cube_ijk_dev, const int64_t* cube_offset_dev, const uint8_t* ijk_dev, const void* pred16_dev,
+                         const uint8_t* init_mask_dev, int n_cubes, int64_t n_vox, int grid_extent, int D_cube, double max_probThresh,
+                         double beta, int n_iter, double* thresh_inout_dev, uint8_t* mask_inout_dev, int32_t* argmin_out_dev,
+                         void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

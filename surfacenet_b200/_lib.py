@@ -50,6 +50,10 @@ SIGNATURES = {
     "sn_dense2sparse_workspace_bytes": (_i64, [_i, _i, _i]),
     "sn_dense2sparse": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _p]),
     "sn_infer_batch_sparse_workspace_bytes": (_i64, [_p, _i, _i, _i, _i, _i]),
+    "sn_sparse_post_workspace_bytes": (_i64, [_i, _i64, _i]),
+    "sn_sparse_filter_voxels": (_i, [_p, _p, _p, _i, _i64, _p, C.c_double, _i, _i, _i, _p, _p, _i64, _p]),
+    "sn_sparse_denoise": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _i64, _p]),
+    "sn_sparse_adapthresh": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, C.c_double, C.c_double, _i, _p, _p, _p, _p, _i64, _p]),
     "sn_infer_batch_sparse": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i, _p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

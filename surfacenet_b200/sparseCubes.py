@@ -1,5 +1,6 @@
 """Drop-in for utils/sparseCubes.py:9-141 (dense2sparse, append_dense_2sparseList): ray pooling, centre crop,
 thresholding and the ordered compaction run on the GPU (sn_raypool_votes, sn_dense2sparse).  "Next" row N1."""
+import os
 import numpy as np
 from . import _lib, rayPooling
 
@@ -119,6 +120,51 @@ def filter_voxels(vxl_mask_list=[], prediction_list=None, prob_thresh=None, rayP
             raise Warning('rayPool_thresh should not be None.')
         _and_into(vxl_mask_list, [v >= rayPool_thresh for v in rayPooling_votes_list])
     return vxl_mask_list
+
+
+def save2ply(ply_filePath, xyz_np, rgb_np=None, normal_np=None):
+    """utils/sparseCubes.py:246-283: binary little-endian PLY with vertex properties x,y,z[,nx,ny,nz][,red,green,blue] (what
+    plyfile's PlyData([PlyElement.describe(saved_pts, 'vertex')]).write() produces for the same structured array)."""
+    xyz_np = np.asarray(xyz_np)
+    N_voxels = xyz_np.shape[0]
+    atributes = [('x', '<f4'), ('y', '<f4'), ('z', '<f4')]
+    if normal_np is not None:
+        atributes += [('nx', '<f4'), ('ny', '<f4'), ('nz', '<f4')]
+    if rgb_np is not None:
+        atributes += [('red', 'u1'), ('green', 'u1'), ('blue', 'u1')]
+    saved_pts = np.zeros(shape=(N_voxels,), dtype=np.dtype(atributes))
+    if N_voxels:
+        saved_pts['x'], saved_pts['y'], saved_pts['z'] = xyz_np[:, 0], xyz_np[:, 1], xyz_np[:, 2]
+        if rgb_np is not None:
+            saved_pts['red'], saved_pts['green'], saved_pts['blue'] = rgb_np[:, 0], rgb_np[:, 1], rgb_np[:, 2]
+        if normal_np is not None:
+            saved_pts['nx'], saved_pts['ny'], saved_pts['nz'] = normal_np[:, 0], normal_np[:, 1], normal_np[:, 2]
+    outputFolder = os.path.dirname(ply_filePath)
+    if outputFolder and not os.path.exists(outputFolder):
+        os.makedirs(outputFolder)
+    names = {'<f4': 'float', 'u1': 'uchar'}
+    header = ["ply", "format binary_little_endian 1.0", "element vertex {}".format(N_voxels)]
+    header += ["property {} {}".format(names[t], n) for n, t in atributes] + ["end_header"]
+    with open(ply_filePath, 'wb') as f:
+        f.write(("\n".join(header) + "\n").encode("ascii"))
+        f.write(saved_pts.tobytes())
+    return 1
+
+
+def save_sparseCubes_2ply(vxl_mask_list, vxl_ijk_list, rgb_list, param, ply_filePath, normal_list=None):
+    """utils/sparseCubes.py:287-327: voxel xyz = ijk * resol + cube xyz (float32) of the masked voxels -> PLY."""
+    vxl_mask_np = np.concatenate([np.asarray(m).astype(bool) for m in vxl_mask_list], axis=0)
+    vxl_ijk_np = np.vstack(vxl_ijk_list)
+    rgb_np = np.vstack(rgb_list)
+    if not vxl_mask_np.shape[0] == vxl_ijk_np.shape[0] == rgb_np.shape[0]:
+        raise Warning('make sure # of voxels in each cube are consistent.')
+    normal_np = None if normal_list is None else np.vstack(normal_list)[vxl_mask_np]
+    xyz_list = []
+    for _cube, _select in enumerate(vxl_mask_list):
+        _select = np.asarray(_select).astype(bool)
+        xyz_list.append(vxl_ijk_list[_cube][_select] * param[_cube]['resol'] + param[_cube]['xyz'][None, :])
+    xyz_np = np.vstack(xyz_list) if xyz_list else np.zeros((0, 3), np.float32)
+    return save2ply(ply_filePath, xyz_np, rgb_np[vxl_mask_np], normal_np)
 
 
 def save_sparseCubes(filePath, prediction_list, rgb_list, vxl_ijk_list, rayPooling_votes_list, cube_ijk_np, param_np, viewPair_np):

@@ -229,3 +229,30 @@ def test_initialize_cubes_matches_reference_log():
     assert np.allclose(c["xyz"][1] - c["xyz"][0], [0, 0, 52 * 0.4 * 0.5], atol=1e-5)
     c, _ = reconstruct.initialize_cubes(np.float32(0.4), 32, 26, 0.5, BB)
     assert len(c) == 40 * 74 * 66
+
+
+def test_save2ply_layout(tmp_path):
+    """utils/sparseCubes.py:246-327: the PLY the N4 consumers write (binary little endian, x y z red green blue)."""
+    from surfacenet_b200 import sparseCubes
+    rs = np.random.RandomState(3)
+    ijk = [rs.randint(0, 52, size=(5, 3)).astype(np.uint8), rs.randint(0, 52, size=(3, 3)).astype(np.uint8)]
+    rgb = [rs.randint(0, 256, size=(5, 3)).astype(np.uint8), rs.randint(0, 256, size=(3, 3)).astype(np.uint8)]
+    mask = [np.array([1, 0, 1, 1, 0], bool), np.array([0, 1, 0], bool)]
+    param = np.zeros(2, util.PARAM_DTYPE)
+    param["xyz"] = [[1.5, -2.0, 600.0], [10.0, 0.0, 610.25]]
+    param["resol"] = np.float32(0.4)
+    path = str(tmp_path / "sub" / "x.ply")
+    assert sparseCubes.save_sparseCubes_2ply(mask, ijk, rgb, param, path) == 1
+    xyz, col = util.read_ply(path)
+    exp = np.vstack([ijk[c][mask[c]] * param[c]["resol"] + param[c]["xyz"][None, :] for c in range(2)]).astype(np.float32)
+    assert xyz.dtype == np.float32 and np.array_equal(xyz, exp)
+    assert np.array_equal(col, np.vstack(rgb)[np.concatenate(mask)])
+    with pytest.raises(Warning):
+        sparseCubes.save_sparseCubes_2ply(mask, ijk, rgb[:1], param, path)
+
+
+def test_post_workspace_and_symbols():
+    from surfacenet_b200 import _lib
+    assert _lib.lib.sn_sparse_post_workspace_bytes(24420, 50000000, 52) > 24420 * (52 ** 3 // 32) * 8
+    assert _lib.lib.sn_sparse_post_workspace_bytes(4, 100, 0) == -1 and _lib.lib.sn_sparse_post_workspace_bytes(4, 100, 257) == -1
+    assert _lib.lib.sn_sparse_post_workspace_bytes(0, 0, 1) > 0

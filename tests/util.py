@@ -169,3 +169,19 @@ def post_cases():
     c["g222_d13_odd_dup"] = dict(scene=sparse_scene((2, 2, 2), 13, seed=3, dup_last=True), init=0.6, maxp=0.8, rp=0, beta=3, iters=3)
     c["g141_d10_thin"] = dict(scene=sparse_scene((1, 4, 1), 10, seed=4, thick=0.04, floaters=12), init=0.5, maxp=0.9, rp=4, beta=6, iters=3)
     return c
+
+
+def read_ply(path):
+    """Minimal reader of the binary little-endian vertex PLY files sparseCubes.save2ply writes -> (xyz f32 (N,3), rgb u8 (N,3) | None)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    lines = raw[:end].decode("ascii").split("\n")
+    assert lines[0] == "ply" and lines[1] == "format binary_little_endian 1.0"
+    n = int([l for l in lines if l.startswith("element vertex")][0].split()[-1])
+    props = [l.split()[1:] for l in lines if l.startswith("property")]
+    dt = np.dtype([(name, {"float": "<f4", "uchar": "u1"}[t]) for t, name in props])
+    v = np.frombuffer(raw[end:], dtype=dt, count=n)
+    xyz = np.stack([v["x"], v["y"], v["z"]], axis=1)
+    rgb = np.stack([v["red"], v["green"], v["blue"]], axis=1) if "red" in dt.names else None
+    return xyz, rgb

@@ -458,13 +458,13 @@ def run_post(args):
     if rank == 0:
         _, hbm_peak, peak_src = peaks()
         # algorithmic bytes per voxel and call: every kernel streams each per-voxel array it needs once
-        #   denoise (10 launches): vox_cube 4 w | bitmap: ijk 3 + mask 1 + vox_cube 4 | init: vox_cube 4 + parent 4 w + ovl 1 w |
-        #     union: ijk 3 + mask 1 + vox_cube 4 | root: vox_cube 4 + parent 4 + root 4 w | overlap: ijk 3 + mask 1 + vox_cube 4 + root 4 |
-        #     keep: ijk 3 + mask 1 + vox_cube 4 + root 4 + ovl 1 + keep 1 w                              = 67 B per voxel
+        #   denoise (11 launches): vox_cube 4 w | bitmap: ijk 3 + mask 1 + vox_cube 4 | link: 8 + parent 4 w | flatten: vox_cube 4 +
+        #     parent 4 r + 4 w | reduce: 8 | root: vox_cube 4 + parent 4 + root 4 w | overlap: ijk 3 + mask 1 + vox_cube 4 + root 4 |
+        #     keep: ijk 3 + mask 1 + vox_cube 4 + root 4 + ovl 1 + keep 1 w | ovl memset 1                = 83 B per voxel
         #   adapthresh iteration (9 launches): vox_cube 4 w + bitmap 8 | occ0: ijk 3 + pred 2 + mask 1 | count: same 6 |
         #     filter: pred 2 + mask 1 + vox_cube 4 + mask 1 w                                             = 32 B per voxel
         #   (the per-cube bitmaps / prefixes, 2 x 17.6 KB per cube, stay in L2 and are not counted)
-        bytes_call = {"denoise": 67.0 * N, "adapthresh_iter": 32.0 * N, "filter": 12.0 * N}
+        bytes_call = {"denoise": 83.0 * N, "adapthresh_iter": 32.0 * N, "filter": 12.0 * N}
         dom = max(("denoise", "adapthresh_iter"), key=lambda k: parts[k])
         dom_ms = parts[dom] / max(n_calls[dom], 1)
         achieved = bytes_call[dom] / (dom_ms * 1e-3) / 1e9
@@ -478,7 +478,7 @@ def run_post(args):
                         "h2d_bytes_per_step": int(N * (3 + 2 + 1) + C * 20), "d2h_bytes_per_step": int(N * (POST_ITERS * 2 + 2) + C * 8),
                         "what": "adapthresh_lists: per-cube numpy lists in, per-iteration masks + denoised masks out (wall clock)"},
                 "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "the %s C-ABI call (%d launches)" % (dom, {"denoise": 10, "adapthresh_iter": 9}[dom]),
+                "roofline": {"bound": "hbm", "kernel": "the %s C-ABI call (%d launches)" % (dom, {"denoise": 11, "adapthresh_iter": 9}[dom]),
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
                              "peak_source": peak_src, "bytes_per_call": bytes_call[dom], "ms_per_call": dom_ms,
                              "calls_ms_per_step": {k: parts[k] for k in parts}, "calls_per_step": n_calls}}

@@ -30,6 +30,7 @@ struct PostWs {
     unsigned long long* hkeys;  // [H]
     int32_t* hvals;        // [H]
     int32_t* canon;        // [C]   1 = this cube is the dict's entry for its ijk (non-empty, last of its key)
+    int32_t* nb27;         // [C*27] dict lookup of cube ijk + shift t (t = (si+1)*9 + (sj+1)*3 + (sk+1)), -1 = none
     int32_t* counts;       // [C*48] adapthresh: n_cur[6][3], n_and[6][3], nb[6], n_half0[6]
     int32_t* flags;        // [4]   error flags
     int64_t W, H;
@@ -58,6 +59,7 @@ static int64_t post_layout(void* ws, int64_t ws_bytes, int n_cubes, int64_t n_vo
     w.hkeys = a.take<unsigned long long>(w.H);
     w.hvals = a.take<int32_t>(w.H);
     w.canon = a.take<int32_t>(C);
+    w.nb27 = a.take<int32_t>(C * 27);
     w.counts = a.take<int32_t>(C * 48);
     w.flags = a.take<int32_t>(4);
     if (out) *out = w;
@@ -155,42 +157,54 @@ __global__ void pp_hash_insert_kernel(const int32_t* __restrict__ cube_ijk, cons
 }
 __global__ void pp_canon_kernel(const int32_t* __restrict__ cube_ijk, const int32_t* __restrict__ n_masked, int n_cubes,
                                 const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t H,
-                                int32_t* __restrict__ canon) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_cubes) return;
-    canon[n] = (n_masked[n] > 0 && pp_lookup(keys, vals, H, cube_ijk[3 * n], cube_ijk[3 * n + 1], cube_ijk[3 * n + 2]) == n) ? 1 : 0;
+                                int32_t* __restrict__ canon, int32_t* __restrict__ nb27) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_cubes * 27) return;
+    const int n = g / 27, t = g % 27;
+    const int m = pp_lookup(keys, vals, H, cube_ijk[3 * n] + t / 9 - 1, cube_ijk[3 * n + 1] + (t / 3) % 3 - 1, cube_ijk[3 * n + 2] + t % 3 - 1);
+    nb27[g] = m;
+    if (t == 13) canon[n] = (n_masked[n] > 0 && m == n) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // connected components (scipy.ndimage.label with generate_binary_structure(3, neighbor_dist))      denoising.py:53-54
-__global__ void pp_ccl_init_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ vox_cube, int64_t n_vox,
-                                   int32_t* __restrict__ parent, uint8_t* __restrict__ ovl) {
-    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_vox) return;
-    parent[v] = (int32_t)(v - off[vox_cube[v]]);
-    ovl[v] = 0;
-}
-
+// Label-equivalence scheme on the raster ranks: (1) every voxel points at its first present neighbour among the 13 that
+// precede it in raster order (a strictly smaller rank, so the forest is acyclic), (2) the chains are flattened, (3) every
+// voxel merges with each preceding neighbour whose root differs (atomicMin hooking, the smaller root wins), (4) final roots.
 __device__ __forceinline__ int pp_find(volatile int32_t* par, int x) {
     int p;
     while ((p = par[x]) != x) x = p;
     return x;
 }
-__device__ __forceinline__ void pp_unite(int32_t* par, int a, int b) {
+// find with path halving: every second node on the way is re-pointed at its grandparent.  Stores race with atomicMin hooks
+// only in the harmless direction (any stored value is an ancestor of the node, ancestors have smaller ranks).
+__device__ __forceinline__ int pp_find_halve(volatile int32_t* par, int x) {
     while (true) {
-        a = pp_find(par, a);
-        b = pp_find(par, b);
-        if (a == b) return;
-        if (a > b) { const int t = a; a = b; b = t; }
-        const int old = atomicMin(&par[b], a);           // hook the larger root under the smaller
-        if (old == b) return;
-        b = old;
+        const int p = par[x];
+        if (p == x) return x;
+        const int gp = par[p];
+        if (gp == p) return p;
+        par[x] = gp;
+        x = gp;
     }
 }
+// merge the trees of a and b (ra = current root of a, kept up to date for the caller)
+__device__ __forceinline__ int pp_unite(int32_t* par, int ra, int b) {
+    int rb = pp_find_halve(par, b);
+    while (ra != rb) {
+        if (ra > rb) { const int t = ra; ra = rb; rb = t; }
+        const int old = atomicMin(&par[rb], ra);         // hook the larger root under the smaller
+        if (old == rb) break;
+        rb = pp_find_halve(par, old);
+        ra = pp_find_halve(par, ra);
+    }
+    return ra < rb ? ra : rb;
+}
 
-__global__ void pp_ccl_union_kernel(const uint8_t* __restrict__ ijk, const uint8_t* __restrict__ mask, const int32_t* __restrict__ vox_cube,
-                                    const int64_t* __restrict__ off, int64_t n_vox, int G, int64_t W, int neighbor_dist,
-                                    const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, int32_t* parent) {
+template <bool REDUCE>
+__global__ void pp_ccl_link_kernel(const uint8_t* __restrict__ ijk, const uint8_t* __restrict__ mask, const int32_t* __restrict__ vox_cube,
+                                   const int64_t* __restrict__ off, int64_t n_vox, int G, int64_t W, int neighbor_dist,
+                                   const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, int32_t* parent) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_vox || !mask[v]) return;
     const int c = vox_cube[v];
@@ -200,16 +214,35 @@ __global__ void pp_ccl_union_kernel(const uint8_t* __restrict__ ijk, const uint8
     const uint32_t* pf = prefix + (int64_t)c * W;
     int32_t* par = parent + off[c];
     const int r = pp_rank(bm, pf, (i * G + j) * G + k);
-    // the 13 neighbours that follow (i,j,k) in raster order; the other 13 are covered from the other side
-    for (int t = 14; t < 27; ++t) {
+    int first = r;
+    int ra = REDUCE ? pp_find_halve(par, r) : r;
+    // 26-connectivity, reduce pass: when the previous voxel of the row (0,0,-1) is occupied, every preceding neighbour with
+    // dk <= 0 is also a preceding neighbour of THAT voxel and gets merged from there; only the four (di,dj,+1) remain.
+    const bool prune = REDUCE && neighbor_dist == 3 && k > 0 && pp_bit(bm, (i * G + j) * G + k - 1);
+    for (int t = 0; t < 13; ++t) {                       // the 13 neighbours that precede (i,j,k) in raster order, smallest first
         const int di = t / 9 - 1, dj = (t / 3) % 3 - 1, dk = t % 3 - 1;
         if ((di != 0) + (dj != 0) + (dk != 0) > neighbor_dist) continue;
+        if (prune && dk != 1 && t != 12) continue;
         const int a = i + di, b = j + dj, cc = k + dk;
         if (a < 0 || b < 0 || cc < 0 || a >= G || b >= G || cc >= G) continue;
         const int q = (a * G + b) * G + cc;
         if (!pp_bit(bm, q)) continue;
-        pp_unite(par, r, pp_rank(bm, pf, q));
+        const int rq = pp_rank(bm, pf, q);
+        if (REDUCE) ra = pp_unite(par, ra, rq);
+        else { first = rq; break; }
     }
+    if (!REDUCE) par[r] = first;
+}
+
+__global__ void pp_ccl_flatten_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ vox_cube, const int32_t* __restrict__ n_masked,
+                                      int64_t n_vox, int32_t* parent) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vox) return;
+    const int c = vox_cube[v];
+    const int r = (int)(v - off[c]);
+    if (r >= n_masked[c]) return;
+    int32_t* par = parent + off[c];
+    par[r] = pp_find(par, r);                            // concurrent writers only ever store ancestors: chains stay valid
 }
 
 __global__ void pp_ccl_root_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ vox_cube, const int32_t* __restrict__ n_masked,
@@ -275,22 +308,20 @@ __global__ void pp_overlap_kernel(const uint8_t* __restrict__ ijk, const uint8_t
                                   const int64_t* __restrict__ off, const int32_t* __restrict__ cube_ijk, const int32_t* __restrict__ canon,
                                   int64_t n_vox, int G, int64_t W, int half, const uint32_t* __restrict__ bitmap,
                                   const uint32_t* __restrict__ prefix, const int32_t* __restrict__ root,
-                                  const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t H,
-                                  uint8_t* __restrict__ ovl) {
+                                  const int32_t* __restrict__ nb27, uint8_t* __restrict__ ovl) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_vox || !mask[v]) return;
     const int n = vox_cube[v];
     if (!canon[n]) return;
     const int i = ijk[3 * v], j = ijk[3 * v + 1], k = ijk[3 * v + 2];
     if (i >= G || j >= G || k >= G) return;
-    const int ci = cube_ijk[3 * n], cj = cube_ijk[3 * n + 1], ck = cube_ijk[3 * n + 2];
     bool hit = false;
     for (int t = 0; t < 27 && !hit; ++t) {
         if (t == 13) continue;
         const int si = t / 9 - 1, sj = (t / 3) % 3 - 1, sk = t % 3 - 1;
         const int a = i - half * si, b = j - half * sj, c = k - half * sk;
         if (a < 0 || b < 0 || c < 0 || a >= G || b >= G || c >= G) continue;
-        const int m = pp_lookup(keys, vals, H, ci + si, cj + sj, ck + sk);
+        const int m = nb27[n * 27 + t];
         if (m < 0) continue;
         hit = pp_bit(bitmap + (int64_t)m * W, (a * G + b) * G + c);
     }
@@ -341,6 +372,8 @@ __device__ __forceinline__ bool pp_in_half(int i, int j, int k, int q, int D, in
 }
 
 // occupancy at the current threshold: bitmap + number of voxels in each half                       adapthresh.py:149-151
+// grid (C, PP_SLICES): a cube's voxel list is dealt to PP_SLICES blocks (a scene has far fewer cubes than the GPU has warps)
+constexpr int PP_SLICES = 8;
 __global__ void __launch_bounds__(PP_THREADS)
 pp_ada_occ0_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ pred, const uint8_t* __restrict__ mask,
                    const int64_t* __restrict__ off, const double* __restrict__ thresh, int G, int64_t W, int D, int Dmid,
@@ -351,17 +384,25 @@ pp_ada_occ0_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ p
     __syncthreads();
     const float thr = __half2float(__double2half(thresh[c]));
     uint32_t* bm = bitmap + (int64_t)c * W;
-    for (int64_t v = off[c] + threadIdx.x; v < off[c + 1]; v += PP_THREADS) {
+    int loc[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t v = off[c] + blockIdx.y * PP_THREADS + threadIdx.x; v < off[c + 1]; v += PP_THREADS * PP_SLICES) {
         if (!mask[v] || !(__half2float(pred[v]) >= thr)) continue;
         const int i = ijk[3 * v], j = ijk[3 * v + 1], k = ijk[3 * v + 2];
         if (i >= G || j >= G || k >= G) { flags[0] = 1; continue; }
         const int pos = (i * G + j) * G + k;
         atomicOr(&bm[pos >> 5], 1u << (pos & 31));
 #pragma unroll
-        for (int q = 0; q < 6; ++q) if (pp_in_half(i, j, k, q, D, Dmid)) atomicAdd(&nh[q], 1);
+        for (int q = 0; q < 6; ++q) loc[q] += pp_in_half(i, j, k, q, D, Dmid) ? 1 : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        int x = loc[q];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&nh[q], x);
     }
     __syncthreads();
-    if (threadIdx.x < 6) counts[c * 48 + 42 + threadIdx.x] = nh[threadIdx.x];
+    if (threadIdx.x < 6 && nh[threadIdx.x]) atomicAdd(&counts[c * 48 + 42 + threadIdx.x], nh[threadIdx.x]);
 }
 
 // per dict cube: for the 6 face neighbours x 3 threshold perturbations, |current half| and |current half AND neighbour half|
@@ -369,16 +410,15 @@ __global__ void __launch_bounds__(PP_THREADS)
 pp_ada_count_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ pred, const uint8_t* __restrict__ mask,
                     const int64_t* __restrict__ off, const int32_t* __restrict__ cube_ijk, const int32_t* __restrict__ canon,
                     const double* __restrict__ thresh, int G, int64_t W, int D, int Dmid, const uint32_t* __restrict__ bitmap,
-                    const unsigned long long* __restrict__ keys, const int32_t* __restrict__ vals, int64_t H, int32_t* __restrict__ counts) {
+                    const int32_t* __restrict__ nb27, int32_t* __restrict__ counts) {
     __shared__ int sc[36];
     __shared__ int nb[6];
     const int n = blockIdx.x;
     if (!canon[n]) return;
     if (threadIdx.x < 36) sc[threadIdx.x] = 0;
     if (threadIdx.x < 6) {
-        const int q = threadIdx.x, s = q < 3 ? 1 : -1, d = q % 3;
-        nb[q] = pp_lookup(keys, vals, H, cube_ijk[3 * n] + (d == 0 ? s : 0), cube_ijk[3 * n + 1] + (d == 1 ? s : 0),
-                          cube_ijk[3 * n + 2] + (d == 2 ? s : 0));
+        const int q = threadIdx.x, sg = q < 3 ? 1 : -1, d = q % 3;                   // shift_q as index into the 27-neighbour table
+        nb[q] = nb27[n * 27 + (1 + (d == 0 ? sg : 0)) * 9 + (1 + (d == 1 ? sg : 0)) * 3 + (1 + (d == 2 ? sg : 0))];
     }
     __syncthreads();
     const double t0 = thresh[n];
@@ -389,7 +429,7 @@ pp_ada_count_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ 
     for (int q = 0; q < 6; ++q)
 #pragma unroll
         for (int t = 0; t < 3; ++t) { ncur[q][t] = 0; nand[q][t] = 0; }
-    for (int64_t v = off[n] + threadIdx.x; v < off[n + 1]; v += PP_THREADS) {
+    for (int64_t v = off[n] + blockIdx.y * PP_THREADS + threadIdx.x; v < off[n + 1]; v += PP_THREADS * PP_SLICES) {
         if (!mask[v]) continue;
         const float p = __half2float(pred[v]);
         const int o0 = p >= thr[0], o1 = p >= thr[1], o2 = p >= thr[2];
@@ -421,8 +461,8 @@ pp_ada_count_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ 
             if ((threadIdx.x & 31) == 0) { if (x) atomicAdd(&sc[q * 3 + t], x); if (y) atomicAdd(&sc[18 + q * 3 + t], y); }
         }
     __syncthreads();
-    if (threadIdx.x < 36) counts[n * 48 + threadIdx.x] = sc[threadIdx.x];
-    if (threadIdx.x < 6) counts[n * 48 + 36 + threadIdx.x] = nb[threadIdx.x];
+    if (threadIdx.x < 36 && sc[threadIdx.x]) atomicAdd(&counts[n * 48 + threadIdx.x], sc[threadIdx.x]);
+    if (threadIdx.x < 6 && blockIdx.y == 0) counts[n * 48 + 36 + threadIdx.x] = nb[threadIdx.x];
 }
 
 // cost accumulation in float16 exactly as numpy 1.13 evaluates `element_cost[t] += int` (float64 sum, rounded to float16 on
@@ -468,7 +508,7 @@ static int post_prepare(const PostWs& w, const int32_t* cube_ijk, const int64_t*
     pp_bitmap_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(ijk, mask, w.vox_cube, n_vox, G, w.W, w.bitmap, w.flags); SN_LAUNCHED();
     pp_prefix_kernel<<<n_cubes, PP_THREADS, 0, st>>>(w.bitmap, w.W, w.prefix, w.n_masked); SN_LAUNCHED();
     pp_hash_insert_kernel<<<pp_grid(n_cubes), PP_THREADS, 0, st>>>(cube_ijk, w.n_masked, n_cubes, w.hkeys, w.hvals, w.H, w.flags); SN_LAUNCHED();
-    pp_canon_kernel<<<pp_grid(n_cubes), PP_THREADS, 0, st>>>(cube_ijk, w.n_masked, n_cubes, w.hkeys, w.hvals, w.H, w.canon); SN_LAUNCHED();
+    pp_canon_kernel<<<pp_grid((int64_t)n_cubes * 27), PP_THREADS, 0, st>>>(cube_ijk, w.n_masked, n_cubes, w.hkeys, w.hvals, w.H, w.canon, w.nb27); SN_LAUNCHED();
     return SN_OK;
 }
 
@@ -527,9 +567,12 @@ extern "C" int sn_sparse_denoise(const int32_t* cube_ijk_dev, const int64_t* cub
     const int G = grid_extent;
     int rc = post_prepare(w, cube_ijk_dev, cube_offset_dev, ijk_dev, mask_dev, n_cubes, n_vox, G, st);
     if (rc != SN_OK) return rc;
-    pp_ccl_init_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(cube_offset_dev, w.vox_cube, n_vox, w.parent, w.ovl); SN_LAUNCHED();
-    pp_ccl_union_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(ijk_dev, mask_dev, w.vox_cube, cube_offset_dev, n_vox, G, w.W, neighbor_dist,
-                                                                w.bitmap, w.prefix, w.parent); SN_LAUNCHED();
+    SN_CUDA(cudaMemsetAsync(w.ovl, 0, (size_t)n_vox, st));
+    pp_ccl_link_kernel<false><<<pp_grid(n_vox), PP_THREADS, 0, st>>>(ijk_dev, mask_dev, w.vox_cube, cube_offset_dev, n_vox, G, w.W, neighbor_dist,
+                                                                      w.bitmap, w.prefix, w.parent); SN_LAUNCHED();
+    pp_ccl_flatten_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(cube_offset_dev, w.vox_cube, w.n_masked, n_vox, w.parent); SN_LAUNCHED();
+    pp_ccl_link_kernel<true><<<pp_grid(n_vox), PP_THREADS, 0, st>>>(ijk_dev, mask_dev, w.vox_cube, cube_offset_dev, n_vox, G, w.W, neighbor_dist,
+                                                                     w.bitmap, w.prefix, w.parent); SN_LAUNCHED();
     pp_ccl_root_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(cube_offset_dev, w.vox_cube, w.n_masked, n_vox, w.parent, w.root); SN_LAUNCHED();
     if (labels_out_dev || n_labels_out_dev) {
         pp_label_rank_kernel<<<n_cubes, PP_THREADS, 0, st>>>(cube_offset_dev, w.n_masked, w.root, w.labelnum, n_labels_out_dev); SN_LAUNCHED();
@@ -540,7 +583,7 @@ extern "C" int sn_sparse_denoise(const int32_t* cube_ijk_dev, const int64_t* cub
     }
     if (keep_out_dev) {
         pp_overlap_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(ijk_dev, mask_dev, w.vox_cube, cube_offset_dev, cube_ijk_dev, w.canon, n_vox, G,
-                                                                  w.W, D_cube / 2, w.bitmap, w.prefix, w.root, w.hkeys, w.hvals, w.H, w.ovl); SN_LAUNCHED();
+                                                                  w.W, D_cube / 2, w.bitmap, w.prefix, w.root, w.nb27, w.ovl); SN_LAUNCHED();
         pp_keep_kernel<<<pp_grid(n_vox), PP_THREADS, 0, st>>>(ijk_dev, mask_dev, w.vox_cube, cube_offset_dev, n_vox, G, w.W, w.bitmap, w.prefix,
                                                                w.root, w.ovl, keep_out_dev); SN_LAUNCHED();
     }
@@ -568,10 +611,11 @@ extern "C" int sn_sparse_adapthresh(const int32_t* cube_ijk_dev, const int64_t* 
     if (rc != SN_OK) return rc;
     for (int it = 0; it < n_iter; ++it) {
         SN_CUDA(cudaMemsetAsync(w.bitmap, 0, (size_t)n_cubes * w.W * 4, st));
-        pp_ada_occ0_kernel<<<n_cubes, PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, thresh_inout_dev, G, w.W, D_cube, Dmid,
+        SN_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)n_cubes * 48 * 4, st));
+        pp_ada_occ0_kernel<<<dim3(n_cubes, PP_SLICES), PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, thresh_inout_dev, G, w.W, D_cube, Dmid,
                                                            w.bitmap, w.counts, w.flags); SN_LAUNCHED();
-        pp_ada_count_kernel<<<n_cubes, PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, cube_ijk_dev, w.canon, thresh_inout_dev,
-                                                            G, w.W, D_cube, Dmid, w.bitmap, w.hkeys, w.hvals, w.H, w.counts); SN_LAUNCHED();
+        pp_ada_count_kernel<<<dim3(n_cubes, PP_SLICES), PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, cube_ijk_dev, w.canon,
+                                                                             thresh_inout_dev, G, w.W, D_cube, Dmid, w.bitmap, w.nb27, w.counts); SN_LAUNCHED();
         pp_ada_update_kernel<<<pp_grid(n_cubes), PP_THREADS, 0, st>>>(w.counts, w.canon, n_cubes, beta, max_probThresh, thresh_inout_dev,
                                                                       argmin_out_dev ? argmin_out_dev + (int64_t)it * n_cubes : nullptr); SN_LAUNCHED();
         if (n_vox > 0) {

@@ -213,25 +213,42 @@ __global__ void pp_ccl_link_kernel(const uint8_t* __restrict__ ijk, const uint8_
     const uint32_t* bm = bitmap + (int64_t)c * W;
     const uint32_t* pf = prefix + (int64_t)c * W;
     int32_t* par = parent + off[c];
-    const int r = pp_rank(bm, pf, (i * G + j) * G + k);
-    int first = r;
-    int ra = REDUCE ? pp_find_halve(par, r) : r;
+    const int pos = (i * G + j) * G + k;
+    // Phase 1 (independent loads, issued together): which of the 13 neighbours that precede (i,j,k) in raster order exist.
     // 26-connectivity, reduce pass: when the previous voxel of the row (0,0,-1) is occupied, every preceding neighbour with
     // dk <= 0 is also a preceding neighbour of THAT voxel and gets merged from there; only the four (di,dj,+1) remain.
-    const bool prune = REDUCE && neighbor_dist == 3 && k > 0 && pp_bit(bm, (i * G + j) * G + k - 1);
-    for (int t = 0; t < 13; ++t) {                       // the 13 neighbours that precede (i,j,k) in raster order, smallest first
+    int q[13];
+#pragma unroll
+    for (int t = 0; t < 13; ++t) {
         const int di = t / 9 - 1, dj = (t / 3) % 3 - 1, dk = t % 3 - 1;
-        if ((di != 0) + (dj != 0) + (dk != 0) > neighbor_dist) continue;
-        if (prune && dk != 1 && t != 12) continue;
         const int a = i + di, b = j + dj, cc = k + dk;
-        if (a < 0 || b < 0 || cc < 0 || a >= G || b >= G || cc >= G) continue;
-        const int q = (a * G + b) * G + cc;
-        if (!pp_bit(bm, q)) continue;
-        const int rq = pp_rank(bm, pf, q);
-        if (REDUCE) ra = pp_unite(par, ra, rq);
-        else { first = rq; break; }
+        const bool ok = ((di != 0) + (dj != 0) + (dk != 0) <= neighbor_dist) && a >= 0 && b >= 0 && cc >= 0 && a < G && b < G && cc < G;
+        const int p = pos + (di * G + dj) * G + dk;
+        q[t] = (ok && pp_bit(bm, p)) ? p : -1;
     }
-    if (!REDUCE) par[r] = first;
+    if (!REDUCE) {
+        int first = -1;
+#pragma unroll
+        for (int t = 12; t >= 0; --t) if (q[t] >= 0) first = q[t];                 // smallest position = smallest rank
+        const int r = pp_rank(bm, pf, pos);
+        par[r] = first >= 0 ? pp_rank(bm, pf, first) : r;
+        return;
+    }
+    if (neighbor_dist == 3 && q[12] >= 0) {
+#pragma unroll
+        for (int t = 0; t < 12; ++t) if (t % 3 != 2) q[t] = -1;
+    }
+    // Phase 2: ranks, Phase 3: current parents (plain loads: a stale parent is still an ancestor, good enough for the filter)
+    int rq[13], pq[13];
+#pragma unroll
+    for (int t = 0; t < 13; ++t) rq[t] = q[t] >= 0 ? pp_rank(bm, pf, q[t]) : -1;
+#pragma unroll
+    for (int t = 0; t < 13; ++t) pq[t] = rq[t] >= 0 ? __ldcg(par + rq[t]) : -1;
+    int ra = pp_find_halve(par, pp_rank(bm, pf, pos));
+    // Phase 4: only neighbours that hang under another node than our root need the (serial, atomic) merge
+#pragma unroll
+    for (int t = 0; t < 13; ++t)
+        if (rq[t] >= 0 && pq[t] != ra) ra = pp_unite(par, ra, rq[t]);
 }
 
 __global__ void pp_ccl_flatten_kernel(const int64_t* __restrict__ off, const int32_t* __restrict__ vox_cube, const int32_t* __restrict__ n_masked,
@@ -316,8 +333,9 @@ __global__ void pp_overlap_kernel(const uint8_t* __restrict__ ijk, const uint8_t
     const int i = ijk[3 * v], j = ijk[3 * v + 1], k = ijk[3 * v + 2];
     if (i >= G || j >= G || k >= G) return;
     bool hit = false;
-    for (int t = 0; t < 27 && !hit; ++t) {
-        if (t == 13) continue;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {                       // unrolled: the shifts are compile-time constants
+        if (t == 13 || hit) continue;
         const int si = t / 9 - 1, sj = (t / 3) % 3 - 1, sk = t % 3 - 1;
         const int a = i - half * si, b = j - half * sj, c = k - half * sk;
         if (a < 0 || b < 0 || c < 0 || a >= G || b >= G || c >= G) continue;
@@ -373,7 +391,7 @@ __device__ __forceinline__ bool pp_in_half(int i, int j, int k, int q, int D, in
 
 // occupancy at the current threshold: bitmap + number of voxels in each half                       adapthresh.py:149-151
 // grid (C, PP_SLICES): a cube's voxel list is dealt to PP_SLICES blocks (a scene has far fewer cubes than the GPU has warps)
-constexpr int PP_SLICES = 8;
+constexpr int PP_SLICES = 8, PP_OCC_SLICES = 32;
 __global__ void __launch_bounds__(PP_THREADS)
 pp_ada_occ0_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ pred, const uint8_t* __restrict__ mask,
                    const int64_t* __restrict__ off, const double* __restrict__ thresh, int G, int64_t W, int D, int Dmid,
@@ -385,7 +403,7 @@ pp_ada_occ0_kernel(const uint8_t* __restrict__ ijk, const __half* __restrict__ p
     const float thr = __half2float(__double2half(thresh[c]));
     uint32_t* bm = bitmap + (int64_t)c * W;
     int loc[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t v = off[c] + blockIdx.y * PP_THREADS + threadIdx.x; v < off[c + 1]; v += PP_THREADS * PP_SLICES) {
+    for (int64_t v = off[c] + blockIdx.y * PP_THREADS + threadIdx.x; v < off[c + 1]; v += PP_THREADS * PP_OCC_SLICES) {
         if (!mask[v] || !(__half2float(pred[v]) >= thr)) continue;
         const int i = ijk[3 * v], j = ijk[3 * v + 1], k = ijk[3 * v + 2];
         if (i >= G || j >= G || k >= G) { flags[0] = 1; continue; }
@@ -612,7 +630,7 @@ extern "C" int sn_sparse_adapthresh(const int32_t* cube_ijk_dev, const int64_t* 
     for (int it = 0; it < n_iter; ++it) {
         SN_CUDA(cudaMemsetAsync(w.bitmap, 0, (size_t)n_cubes * w.W * 4, st));
         SN_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)n_cubes * 48 * 4, st));
-        pp_ada_occ0_kernel<<<dim3(n_cubes, PP_SLICES), PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, thresh_inout_dev, G, w.W, D_cube, Dmid,
+        pp_ada_occ0_kernel<<<dim3(n_cubes, PP_OCC_SLICES), PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, thresh_inout_dev, G, w.W, D_cube, Dmid,
                                                            w.bitmap, w.counts, w.flags); SN_LAUNCHED();
         pp_ada_count_kernel<<<dim3(n_cubes, PP_SLICES), PP_THREADS, 0, st>>>(ijk_dev, pred, mask_inout_dev, cube_offset_dev, cube_ijk_dev, w.canon,
                                                                              thresh_inout_dev, G, w.W, D_cube, Dmid, w.bitmap, w.nb27, w.counts); SN_LAUNCHED();

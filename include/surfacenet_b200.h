@@ -247,6 +247,42 @@ int sn_sparse_adapthresh(const int32_t* cube_ijk_dev, const int64_t* cube_offset
                          double beta, int n_iter, double* thresh_inout_dev, uint8_t* mask_inout_dev, int32_t* argmin_out_dev,
                          void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row N3: the producers of the selected view pairs and their weights.
+ *
+ * utils/camera.py:275-309  viewPairAngles_wrt_pts(cameraTs, pts_xyz) -> (n_pts, n_pairs) angles; everything float32
+ *   (is_f64 == 0) or float64 (the reference computes in the promoted dtype of its inputs); viewpairs_dev (n_pairs,2) i32. */
+int sn_viewpair_angles(const void* cameraTs_dev, const void* pts_dev, int n_views, int64_t n_pts, const int32_t* viewpairs_dev,
+                       int n_pairs, int is_f64, void* out_dev, void* stream);
+/* utils/viewPairSelection.py:70-74  rows [e[c,v1,:], e[c,v2,:], dissimilarity[c,q], angle[c,q]] as float32:
+ *   emb_dev (n_cubes, n_views, E) f32, dissim_dev (n_cubes, n_pairs) f32, theta_dev (n_cubes, n_pairs) f32|f64
+ *   -> out_dev (n_cubes*n_pairs, 2E+2) f32, the input of sn_net_relative_importance */
+int sn_viewpair_features(const float* emb_dev, const int32_t* viewpairs_dev, const float* dissim_dev, const void* theta_dev,
+                         int theta_is_f64, int64_t n_cubes, int n_views, int n_pairs, int D_embedding, float* out_dev, void* stream);
+/* utils/viewPairSelection.py:36  w.argsort(axis=1)[:, -N:]: per row the indices of the N largest values, ascending by value
+ *   (equal values in index order; numpy leaves ties unspecified).  w_dev (n_rows, n) f64, n <= 4096 -> idx_out_dev (n_rows, N) i32 */
+int sn_topn_rows(const double* w_dev, int64_t n_rows, int n, int N, int32_t* idx_out_dev, void* stream);
+/* utils/earlyRejection.py:82-93  selectFromSimilarity: ((d < 0.5) & (d > 0.1)).sum(axis=1) >= N -> out_dev (n_cubes) u8 */
+int sn_select_from_similarity(const float* dissim_dev, int64_t n_cubes, int n_pairs, int N, uint8_t* out_dev, void* stream);
+/* utils/image.py:92-200 cropImgPatches(pyramidRate=1, cubeCenter_hw=...) fused with preprocess_patches (image.py:9-48):
+ *   image_dev (H,W,3) u8 RGB; centres (n) f64 -> out_dev (n, 3, patch, patch) f32 in BGR order minus mean_bgr_dev (3) */
+int sn_crop_patches(const uint8_t* image_dev, int H, int W, const double* center_h_dev, const double* center_w_dev, int64_t n,
+                    int patch, const float* mean_bgr_dev, float* out_dev, void* stream);
+
+/* nets/similarityNet.py:234-246  similarityNet_inference(model_file, imgPatch_hw_size) -> (patch2embedding_fn, embeddingPair2simil_fn)
+ *   sn_simnet_create: the 30 arrays of lasagne.layers.get_all_param_values([embedding, similarity]): 13 x (conv W (Cout,Cin,3,3), b),
+ *   dense W (5888,128), b (128), similarity W (1,1), b (1).  patch must be 64 (params.py:93). */
+typedef struct sn_simnet sn_simnet;
+int  sn_simnet_create(const float* const* arrays_host, const int64_t* sizes, int n_arrays, int patch, sn_simnet** out);
+void sn_simnet_destroy(sn_simnet* net);
+int64_t sn_simnet_workspace_bytes(const sn_simnet* net, int64_t n_patches);
+/* patch2embedding_fn: patches_dev (n, 3, 64, 64) f32 (BGR, mean subtracted) -> emb_out_dev (n, 128) f32   similarityNet.py:23-56 */
+int sn_simnet_patch2embedding(const sn_simnet* net, const float* patches_dev, int64_t n_patches, float* emb_out_dev,
+                              void* workspace_dev, int64_t workspace_bytes, void* stream);
+/* embeddingPair2simil_fn: rows (2m, 2m+1) of embedding_pairs_dev (2*n_pairs, E) f32 -> out_dev (n_pairs) f32   similarityNet.py:66-77 */
+int sn_simnet_embeddingpair2simil(const sn_simnet* net, const float* embedding_pairs_dev, int64_t n_pairs, int D_embedding,
+                                  float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

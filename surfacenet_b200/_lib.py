@@ -54,6 +54,16 @@ SIGNATURES = {
     "sn_sparse_filter_voxels": (_i, [_p, _p, _p, _i, _i64, _p, C.c_double, _i, _i, _i, _p, _p, _i64, _p]),
     "sn_sparse_denoise": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _p, _p, _p, _p, _i64, _p]),
     "sn_sparse_adapthresh": (_i, [_p, _p, _p, _p, _p, _i, _i64, _i, _i, C.c_double, C.c_double, _i, _p, _p, _p, _p, _i64, _p]),
+    "sn_viewpair_angles": (_i, [_p, _p, _i, _i64, _p, _i, _i, _p, _p]),
+    "sn_viewpair_features": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _p, _p]),
+    "sn_topn_rows": (_i, [_p, _i64, _i, _i, _p, _p]),
+    "sn_select_from_similarity": (_i, [_p, _i64, _i, _i, _p, _p]),
+    "sn_crop_patches": (_i, [_p, _i, _i, _p, _p, _i64, _i, _p, _p, _p]),
+    "sn_simnet_create": (_i, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _i, _i, C.POINTER(C.c_void_p)]),
+    "sn_simnet_destroy": (None, [_p]),
+    "sn_simnet_workspace_bytes": (_i64, [_p, _i64]),
+    "sn_simnet_patch2embedding": (_i, [_p, _p, _i64, _p, _p, _i64, _p]),
+    "sn_simnet_embeddingpair2simil": (_i, [_p, _p, _i64, _i, _p, _p]),
     "sn_infer_batch_sparse": (_i, [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i, _p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

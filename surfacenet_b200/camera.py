@@ -1,4 +1,5 @@
-"""Drop-in for utils/camera.py:123-184 perspectiveProj, evaluated on the GPU (sn_perspective_proj)."""
+"""Drop-ins for utils/camera.py: perspectiveProj (123-184, sn_perspective_proj) and viewPairAngles_wrt_pts (275-309,
+sn_viewpair_angles), evaluated on the GPU."""
 import numpy as np
 from . import _lib
 
@@ -34,3 +35,22 @@ def perspectiveProj(projection_M, xyz_3D, return_int_hw=True, return_depth=False
         d = d.cpu().numpy()
         return h, w, (d[0] if single else d)
     return h, w
+
+
+def viewPairAngles_wrt_pts(cameraTs, pts_xyz, viewPairs=None, device_out=False):
+    """utils/camera.py:275-309: angle <camera_i, point, camera_j> for every point and every 2-combination of cameras (or the given
+    viewPairs) -> (N_pts, N_viewPairs), in the promoted dtype of the inputs (float32 only when both are float32)."""
+    from .utils import k_combination_np
+    torch = _lib.require_cuda()
+    cameraTs, pts_xyz = np.asarray(cameraTs), np.asarray(pts_xyz)
+    if cameraTs.ndim != 2 or cameraTs.shape[1] != 3 or pts_xyz.ndim != 2 or pts_xyz.shape[1] != 3:
+        raise ValueError("need cameraTs (N_views,3) and pts_xyz (N_pts,3), got {} {}".format(cameraTs.shape, pts_xyz.shape))
+    dt = np.float32 if (cameraTs.dtype == np.float32 and pts_xyz.dtype == np.float32) else np.float64
+    pairs = k_combination_np(range(cameraTs.shape[0]), k=2) if viewPairs is None else np.asarray(viewPairs)
+    cam = torch.from_numpy(np.ascontiguousarray(cameraTs, dtype=dt)).cuda()
+    pts = torch.from_numpy(np.ascontiguousarray(pts_xyz, dtype=dt)).cuda()
+    vp = torch.from_numpy(np.ascontiguousarray(pairs.reshape(-1, 2), dtype=np.int32)).cuda()
+    out = torch.empty((pts.shape[0], vp.shape[0]), dtype=torch.float64 if dt == np.float64 else torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_viewpair_angles(_lib.ptr(cam), _lib.ptr(pts), cam.shape[0], pts.shape[0], _lib.ptr(vp), vp.shape[0],
+                                           1 if dt == np.float64 else 0, _lib.ptr(out), _lib.stream_ptr()))
+    return out if device_out else out.cpu().numpy()

@@ -3,6 +3,8 @@ path: batches of cubes go through HotPath.infer_batch_sparse (CVC -> SurfaceNet 
 centre crop / threshold / compaction, all on the GPU), the per-cube sparse lists are accumulated exactly as
 sparseCubes.append_dense_2sparseList would, thresholded with (tau, gamma) and written in the reference's NPZ schema.
 
+`finish` adds what follows the loop (main_reconstruct.py:168-183): fixed-threshold masks, cross-cube denoising on the GPU, PLY + NPZ.
+
 What comes BEFORE this section in the reference (image / camera loading, early rejection with similarityNet, view-pair
 selection) is out of scope: the caller passes the selected view pairs and their weights.
 """
@@ -64,13 +66,18 @@ def reconstruct_cubes(hot, cubes_param, viewPairs, w, cube_D, cube_Dcenter=None,
     return lists + (cube_ijk_np, param_np, viewPair_np)
 
 
-def finish(result, npz_path=None, tau=TAU, gamma=GAMMA):
-    """main_reconstruct.py:170-183 without the cross-cube denoising and the PLY writer (out of scope): the fixed-threshold
-    mask `prediction >= tau & votes >= gamma * N_vp * 2`, and the NPZ file adapthresh / load_sparseCubes read back."""
+def finish(result, npz_path=None, ply_path=None, tau=TAU, gamma=GAMMA, cube_D=64):
+    """main_reconstruct.py:168-183: the fixed-threshold mask `prediction >= tau & votes >= gamma * N_vp * 2`, the cross-cube
+    denoising (GPU, surfacenet_b200.denoising; D_cube = cube_D exactly as the reference passes it at :173), the PLY of the
+    denoised cloud and the NPZ file adapthresh / load_sparseCubes read back.  -> (vxl_mask_list, vxl_maskDenoised_list)"""
+    from . import denoising
     prediction_list, rgb_list, vxl_ijk_list, votes_list, cube_ijk_np, param_np, viewPair_np = result
     n_vp = viewPair_np.shape[1]
     masks = sparseCubes.filter_voxels(vxl_mask_list=[], prediction_list=prediction_list, prob_thresh=tau,
                                       rayPooling_votes_list=votes_list, rayPool_thresh=gamma * n_vp * 2)
+    denoised = denoising.denoise_crossCubes(cube_ijk_np, vxl_ijk_list, vxl_mask_list=masks, D_cube=cube_D)
+    if ply_path is not None:
+        sparseCubes.save_sparseCubes_2ply(denoised, vxl_ijk_list, rgb_list, param_np, ply_filePath=ply_path, normal_list=None)
     if npz_path is not None:
         sparseCubes.save_sparseCubes(npz_path, *result)
-    return masks
+    return masks, denoised

@@ -31,3 +31,9 @@ def generate_voxelLevelWeighted_coloredCubes(viewPair_coloredCubes, viewPair_sur
         raise ValueError("weight4viewPair must have shape {}, got {}".format(p.shape[:2], w.shape))
     f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
     return color_fusion_device(f32(viewPair_coloredCubes), f32(p), f32(w)).cpu().numpy()
+
+
+def k_combination_np(iterable, k=2):
+    """utils/utils.py:233-256: all k-combinations of `iterable` as the rows of an array (host index bookkeeping)."""
+    import itertools
+    return np.asarray(list(itertools.combinations(iterable, k)))

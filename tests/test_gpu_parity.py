@@ -489,10 +489,17 @@ def test_reconstruct_cubes_batching_and_npz(torch_cuda, params, cams, tmp_path):
     got = sorted(tuple(x) for p in parts if p != "Empty!" for x in p[4].tolist())
     assert got == sorted(tuple(x) for x in ref[4].tolist())
     f = str(tmp_path / "model.npz")
-    masks = reconstruct.finish(res, f)
+    ply = str(tmp_path / "fixThresh.ply")
+    masks, denoised = reconstruct.finish(res, f, ply_path=ply, tau=0.5, gamma=0.0, cube_D=D)
     back = sparseCubes.load_sparseCubes(f)
     assert all(np.array_equal(x, y) for x, y in zip(back[0], res[0])) and np.array_equal(back[5]["xyz"], res[5]["xyz"])
     assert len(masks) == len(res[0]) and masks[0].dtype == bool
+    from oracle import postprocess_oracle as post                              # main_reconstruct.py:170-176 on the CPU
+    m_o = post.filter_voxels([], res[0], 0.5, res[3], 0.0)
+    d_o = post.denoise_crossCubes(res[4], res[2], m_o, D)
+    assert all(np.array_equal(a, b) for a, b in zip(masks, m_o)) and all(np.array_equal(a, b) for a, b in zip(denoised, d_o))
+    xyz_ply, _ = util.read_ply(ply)
+    assert xyz_ply.shape[0] == int(sum(d.sum() for d in denoised))
     assert reconstruct.reconstruct_cubes(hot, cubes[:0], pairs[:0], w[:0], D, Dc) == "Empty!"
 
 

@@ -1,0 +1,155 @@
+"""GPU parity tests of the "next" row N3: view-pair angles, feature assembly + relative-importance + top-N selection, early rejection
+(patch cropping, similarityNet embedding, pair dissimilarity, cube selection) against the reference's doctest known answers, golden
+vectors produced by the reference's numpy code, and the torch-CPU oracle of the similarityNet.
+Bars: bit-exact for index / uint8 work and the crop+preprocess arithmetic; floating point tolerances written at each assert."""
+import math
+import os
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(util.REPO, "tests", "golden", "select_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def case(cams):
+    return util.select_case(cams)
+
+
+def test_viewPairAngles_reference_doctest_and_golden(g, case):
+    from surfacenet_b200 import camera
+    pts = np.array([[0, 0, 0], [1, 1, 1]], dtype=np.float32)           # utils/camera.py:290-294
+    cT = np.array([[0, 0, 1], [0, 1, 1], [1, 0, 1]], dtype=np.float32)
+    a = camera.viewPairAngles_wrt_pts(cT, pts)
+    assert a.dtype == np.float32 and np.allclose(a * 180 / math.pi, [[45., 45., 60.], [45., 45., 90.]], atol=1e-4)
+    assert np.abs(a - g["ang_doc"]).max() <= 2e-7                      # float32 acos: <= 2 ulp of pi/2
+    cTs = g["cameraTs"][case["views"]]
+    a64 = camera.viewPairAngles_wrt_pts(cTs, case["centers"].astype(np.float32))
+    assert a64.dtype == np.float64 and np.abs(a64 - g["ang_dtu64"]).max() <= 1e-14
+    a32 = camera.viewPairAngles_wrt_pts(cTs.astype(np.float32), case["centers"].astype(np.float32))
+    assert a32.dtype == np.float32 and np.abs(a32 - g["ang_dtu32"]).max() <= 2e-7
+    with pytest.raises(ValueError):
+        camera.viewPairAngles_wrt_pts(np.zeros((3, 2)), pts)
+
+
+def test_argmaxN_viewPairs_reference_doctest_and_golden(g, case):
+    from surfacenet_b200 import viewPairSelection as vps
+    from surfacenet_b200.utils import k_combination_np
+    vp = k_combination_np(range(3), k=2)                               # utils/viewPairSelection.py:17-31
+    w = np.array([[3, 1, 2], [0, -1, 70]])
+    a, b = vps.__argmaxN_viewPairs__(vp, w, 1)
+    assert a.tolist() == [[[0, 1]], [[1, 2]]] and b.tolist() == [[3], [70]]
+    a, b = vps.__argmaxN_viewPairs__(vp, w, 2)
+    assert a.tolist() == [[[1, 2], [0, 1]], [[0, 1], [1, 2]]] and b.tolist() == [[2, 3], [0, 70]]
+    a, b = vps.__argmaxN_viewPairs__(case["viewPairs"], case["w_rand"], 5)
+    assert np.array_equal(a, g["argmax_rand_pairs"]) and np.array_equal(b, g["argmax_rand_w"])
+    # 1176 pairs (49 views), N = 5: against numpy's argsort on a large random matrix
+    rs = np.random.RandomState(5)
+    big = rs.rand(37, 1176).astype(np.float32)
+    vp49 = k_combination_np(range(49), k=2)
+    a, b = vps.__argmaxN_viewPairs__(vp49, big, 5)
+    idx = np.argsort(big, axis=1, kind="stable")[:, -5:]
+    assert np.array_equal(a, vp49[idx]) and np.array_equal(b, np.take_along_axis(big, idx, axis=1))
+    with pytest.raises(ValueError):
+        vps.__argmaxN_viewPairs__(vp, w, 4)
+
+
+def test_crop_and_preprocess_bit_exact(g, case):
+    from surfacenet_b200 import image
+    img = util.synth_image(3, 300, 400)
+    p = image.cropImgPatches(img, case["range_h"], case["range_w"], patchSize=64, pyramidRate=1, interp_order=2,
+                             cubeCenter_hw=(case["crop_ch"], case["crop_cw"]))
+    assert p.dtype == np.uint8 and np.array_equal(p, g["crop_patches"])
+    assert np.array_equal(image.preprocess_patches(np.zeros((2, 2, 5, 3)), np.array([1, 2, 3])), g["pre_doc"])
+    with pytest.raises(ValueError):
+        image.cropImgPatches(img, case["range_h"], case["range_w"], pyramidRate=1.2)
+
+
+def test_early_rejection_matches_reference_outputs(g, case):
+    """The reference's earlyRejection functions were run with deterministic stand-in networks; the same stand-ins (numpy callables)
+    are plugged into the GPU drop-ins, so cropping / preprocessing / scatter / pair enumeration / selection are compared exactly."""
+    import torch
+    from surfacenet_b200 import earlyRejection as er
+    def emb_fn(p):                                                       # accepts numpy or cuda tensors like the real callable
+        if torch.is_tensor(p):
+            return torch.from_numpy(util.fake_patch2embedding_fn(p.cpu().numpy())).cuda()
+        return util.fake_patch2embedding_fn(p)
+    def pair_fn(p):
+        return torch.from_numpy(util.fake_pair2simil_fn(p.cpu().numpy())).cuda()
+    emb, inscope = er.patch2embedding(case["images"], case["h_corner"], case["w_corner"], emb_fn, util.MEAN_BGR, case["N_cubes"],
+                                      len(case["views"]), 16, patchSize=64, batchSize=5, cubeCenter_hw=case["center_hw"])
+    assert np.array_equal(inscope, g["er_inscope"]) and np.array_equal(emb, g["er_emb"])
+    dis = er.embeddingPairs2simil(emb, len(case["views"]), inscope, pair_fn, 7, case["viewPairs"])
+    assert np.array_equal(dis, g["er_dissim"])
+    assert np.array_equal(er.selectFromSimilarity(dis, 3), g["er_select"])
+    assert np.array_equal(er.selectFromSimilarity(g["er_dissim"], 0), np.ones(case["N_cubes"], bool))
+
+
+def test_similarityNet_vs_oracle(case):
+    from oracle import selection_oracle as so
+    from surfacenet_b200 import similarityNet
+    params = similarityNet.synthetic_params(0)
+    p2e, pair = similarityNet.similarityNet_inference(params, (64, 64))
+    rs = np.random.RandomState(1)
+    img = util.synth_image(7, 400, 500)
+    patches = so.preprocess_patches(so.cropImgPatches_rate1(img, 64, (rs.rand(9) * 400, rs.rand(9) * 500)).astype(np.float32), util.MEAN_BGR)
+    patches = np.concatenate([patches, so.preprocess_patches(np.zeros((1, 64, 64, 3), np.float32), util.MEAN_BGR)])
+    e = p2e(np.ascontiguousarray(patches, np.float32))
+    e_o = so.patch2embedding_fn(patches, params)
+    assert e.shape == (10, 128) and e.dtype == np.float32
+    scale = np.abs(e_o).max()
+    assert np.abs(e - e_o).max() <= 1e-4 * scale, (np.abs(e - e_o).max(), scale)      # fp32 FMA vs torch-CPU fp32, 13 conv layers deep
+    pairs = np.ascontiguousarray(e_o[[0, 1, 2, 3, 4, 4, 9, 0]], np.float32)
+    s = pair(pairs)
+    s_o = so.embeddingPair2simil_fn(pairs, params)
+    assert s.shape == (4, 1) and np.abs(s - s_o).max() <= 1e-6
+    assert abs(float(s[2, 0]) - 1.0 / (1.0 + math.exp(-2.0))) <= 1e-6               # identical embeddings: distance 0 -> sigmoid(b)
+    with pytest.raises(ValueError):
+        p2e(np.zeros((2, 3, 32, 32), np.float32))
+    with pytest.raises(ValueError):
+        similarityNet.similarityNet_inference(params[:-1], (64, 64))
+
+
+def test_viewPairSelection_vs_reference_output(g, case):
+    """Reference viewPairSelection was run with the oracle's relative-importance MLP; here the GPU MLP (sn_net_relative_importance)
+    produces the weights: same selected pairs, weights within 1e-5."""
+    from surfacenet_b200 import SurfaceNet, viewPairSelection as vps, weights
+    fn, _ = SurfaceNet.SurfaceNet_inference(4, weights.synthetic_params(0))
+    selp, w = vps.viewPairSelection(g["cameraTs"][case["views"]], g["vps_e"], g["vps_d"], g["vps_valid"], case["centers"].astype(np.float32), fn,
+                                    4 * case["viewPairs"].shape[0] + 3, 4, case["viewPairs"])
+    assert w.shape == g["vps_w"].shape and np.abs(w - g["vps_w"]).max() <= 1e-5
+    gaps = np.diff(np.sort(g["vps_w"], axis=1), axis=1).min()
+    if gaps > 1e-5:                                                    # well separated weights: the discrete choice must agree
+        assert np.array_equal(selp, g["vps_sel"])
+
+
+def test_end_to_end_early_rejection_and_selection_vs_oracle(case, g):
+    """similarityNet embeddings -> dissimilarity -> valid cubes -> view pairs + weights, GPU drop-ins vs the oracle chain."""
+    from oracle import selection_oracle as so, surfacenet_oracle
+    from surfacenet_b200 import SurfaceNet, earlyRejection as er, similarityNet, viewPairSelection as vps, weights
+    sp = similarityNet.synthetic_params(0)
+    p2e, pair = similarityNet.similarityNet_inference(sp, (64, 64))
+    imgs, V = case["images"][:3], 3
+    args = (imgs, case["h_corner"][:V], case["w_corner"][:V])
+    emb, inscope = er.patch2embedding(*args, p2e, util.MEAN_BGR, case["N_cubes"], V, 128, patchSize=64, batchSize=16, cubeCenter_hw=case["center_hw"][:, :V])
+    emb_o, inscope_o = so.patch2embedding(*args, lambda p: so.patch2embedding_fn(p, sp), util.MEAN_BGR, case["N_cubes"], V, 128, 64, 16, case["center_hw"][:, :V])
+    assert np.array_equal(inscope, inscope_o)
+    assert np.abs(emb - emb_o).max() <= 1e-4 * np.abs(emb_o).max()
+    vp = so.k_combination_np(range(V), 2)
+    dis = er.embeddingPairs2simil(emb, V, inscope, pair, 1000, vp)
+    dis_o = so.embeddingPairs2simil(emb_o, V, lambda p: so.embeddingPair2simil_fn(p, sp), 1000)
+    assert dis.shape == (case["N_cubes"], 3) and np.abs(dis - dis_o).max() <= 1e-4
+    valid = np.ones(case["N_cubes"], bool)
+    params = weights.synthetic_params(0)
+    fn, _ = SurfaceNet.SurfaceNet_inference(2, params)
+    cT = g["cameraTs"][case["views"][:V]]
+    selp, w = vps.viewPairSelection(cT, emb, dis, valid, case["centers"].astype(np.float32), fn, 100, 2, vp)
+    fo = lambda f, n_samples_perGroup: surfacenet_oracle.viewPair_relativeImpt_fn(f, params, n_samples_perGroup)
+    selo, wo = so.viewPairSelection(cT, emb_o, dis_o, valid, case["centers"].astype(np.float32), fo, 100, 2, vp)
+    assert np.abs(w - wo).max() <= 1e-3 and selp.shape == selo.shape == (case["N_cubes"], 2, 2)

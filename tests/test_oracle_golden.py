@@ -209,3 +209,59 @@ def test_postprocess_oracle_matches_reference_outputs(post_golden, name):
     for i, it in enumerate(res["iters"]):
         assert np.array_equal(it["probThresh"], g("ada_thresh")[i])
         assert np.array_equal(cat(it["denoised"]).astype(np.uint8), g("ada_denoised")[i])
+
+
+# ---- "next" row N3: view-pair angles / selection / early rejection host code ------------------------------------------------
+from oracle import selection_oracle as sel
+
+
+@pytest.fixture(scope="module")
+def select_golden():
+    import os
+    return np.load(os.path.join(util.REPO, "tests", "golden", "select_golden.npz"))
+
+
+def test_viewPairAngles_reference_doctest_known_answers(select_golden, cams):
+    import math                                                        # utils/camera.py:290-294
+    pts = np.array([[0, 0, 0], [1, 1, 1]], dtype=np.float32)
+    cT = np.array([[0, 0, 1], [0, 1, 1], [1, 0, 1]], dtype=np.float32)
+    a = sel.viewPairAngles_wrt_pts(cT, pts)
+    assert a.dtype == np.float32 and np.allclose(a * 180 / math.pi, [[45., 45., 60.], [45., 45., 90.]], atol=1e-4)
+    assert np.array_equal(a, select_golden["ang_doc"])
+    case = util.select_case(cams)
+    cTs = select_golden["cameraTs"][case["views"]]
+    assert np.array_equal(sel.viewPairAngles_wrt_pts(cTs, case["centers"].astype(np.float32)), select_golden["ang_dtu64"])
+    assert np.array_equal(sel.viewPairAngles_wrt_pts(cTs.astype(np.float32), case["centers"].astype(np.float32)), select_golden["ang_dtu32"])
+
+
+def test_argmaxN_viewPairs_reference_doctest_known_answers(select_golden, cams):
+    vp = sel.k_combination_np(range(3), k=2)                           # utils/viewPairSelection.py:17-31
+    w = np.array([[3, 1, 2], [0, -1, 70]])
+    a, b = sel.argmaxN_viewPairs(vp, w, 1)
+    assert a.tolist() == [[[0, 1]], [[1, 2]]] and b.tolist() == [[3], [70]]
+    a, b = sel.argmaxN_viewPairs(vp, w, 2)
+    assert a.tolist() == [[[1, 2], [0, 1]], [[0, 1], [1, 2]]] and b.tolist() == [[2, 3], [0, 70]]
+    case = util.select_case(cams)
+    a, b = sel.argmaxN_viewPairs(case["viewPairs"], case["w_rand"], 5)
+    assert np.array_equal(a, select_golden["argmax_rand_pairs"]) and np.array_equal(b, select_golden["argmax_rand_w"])
+
+
+def test_selection_oracle_matches_reference_outputs(select_golden, cams):
+    case = util.select_case(cams)
+    g = select_golden
+    assert np.array_equal(sel.preprocess_patches(np.zeros((2, 2, 5, 3)), np.array([1, 2, 3])), g["pre_doc"])
+    img = util.synth_image(3, 300, 400)
+    assert np.array_equal(sel.cropImgPatches_rate1(img, 64, (case["crop_ch"], case["crop_cw"])), g["crop_patches"])
+    emb, inscope = sel.patch2embedding(case["images"], case["h_corner"], case["w_corner"], util.fake_patch2embedding_fn, util.MEAN_BGR,
+                                       case["N_cubes"], len(case["views"]), 16, 64, 5, case["center_hw"])
+    assert np.array_equal(inscope, g["er_inscope"]) and np.array_equal(emb, g["er_emb"])
+    dis = sel.embeddingPairs2simil(emb, len(case["views"]), util.fake_pair2simil_fn, 7)
+    assert np.array_equal(dis, g["er_dissim"])
+    assert np.array_equal(sel.selectFromSimilarity(dis, 3), g["er_select"]) and 0 < g["er_select"].sum() < case["N_cubes"]
+    from oracle import surfacenet_oracle
+    from surfacenet_b200 import weights
+    params = weights.synthetic_params(0)
+    fn = lambda f, n_samples_perGroup: surfacenet_oracle.viewPair_relativeImpt_fn(f, params, n_samples_perGroup)
+    s, w = sel.viewPairSelection(g["cameraTs"][case["views"]], g["vps_e"], g["vps_d"], g["vps_valid"], case["centers"].astype(np.float32), fn,
+                                 4 * case["viewPairs"].shape[0] + 3, 4, case["viewPairs"])
+    assert np.array_equal(s, g["vps_sel"]) and np.array_equal(w, g["vps_w"])

@@ -185,3 +185,47 @@ def read_ply(path):
     xyz = np.stack([v["x"], v["y"], v["z"]], axis=1)
     rgb = np.stack([v["red"], v["green"], v["blue"]], axis=1) if "red" in dt.names else None
     return xyz, rgb
+
+
+# ---- "next" row N3: early rejection / view-pair selection -----------------------------------------------------------------
+MEAN_BGR = np.asarray([103.939, 116.779, 123.68], dtype=np.float32)                           # params.py:131
+
+
+def fake_patch2embedding_fn(patches):
+    """Deterministic stand-in for the similarityNet embedding: 16 fixed linear functionals of the (N,3,64,64) patch."""
+    p = np.asarray(patches, np.float32)
+    rs = np.random.RandomState(9)
+    A = rs.randn(16, 3, 8, 8).astype(np.float32) / 64.0
+    pooled = p.reshape(p.shape[0], 3, 8, 8, 8, 8).mean(axis=(3, 5), dtype=np.float64)
+    return np.einsum("ncij,kcij->nk", pooled, A.astype(np.float64)).astype(np.float32)
+
+
+def fake_pair2simil_fn(pairs):
+    e = np.asarray(pairs, np.float64).reshape(-1, 2, pairs.shape[-1])
+    d = np.sqrt(((e[:, 0] - e[:, 1]) ** 2).sum(axis=1, keepdims=True))
+    return (1.0 / (1.0 + np.exp(-(0.02 * d - 1.2)))).astype(np.float32)
+
+
+def select_case(cams):
+    """6 views of small synthetic images, a 3x3x2 grid of cube centres around the scan9 volume, their projected corners."""
+    rs = np.random.RandomState(31)
+    views = np.array([3, 8, 15, 22, 30, 41])
+    centers = np.array([[x, y, z] for x in (-20.0, 10.0, 40.0) for y in (-40.0, 0.0, 40.0) for z in (600.0, 660.0)], np.float64)
+    N = centers.shape[0]
+    half = 12.8
+    corners = centers[:, None, :] + half * np.array([[a, b, c] for a in (-1, 1) for b in (-1, 1) for c in (-1, 1)], np.float64)[None]
+    P = cams[views]
+    def proj(pts):                                   # camera.perspectiveProj arithmetic (float64), h = row, w = column
+        ph = np.concatenate([pts, np.ones((pts.shape[0], 1))], axis=1)
+        q = np.matmul(P, ph.T)                        # (V,3,n)
+        return q[:, 1] / q[:, 2], q[:, 0] / q[:, 2]
+    h_c, w_c = proj(corners.reshape(-1, 3))
+    h_corner, w_corner = h_c.reshape(len(views), N, 8), w_c.reshape(len(views), N, 8)
+    ch, cw = proj(centers)
+    images = [synth_image(100 + int(v), 1200 if i % 2 == 0 else 900, 1600 if i % 3 else 1100) for i, v in enumerate(views)]
+    viewPairs = np.asarray([(a, b) for a in range(len(views)) for b in range(a + 1, len(views))])
+    n_crop = 7
+    return dict(views=views, centers=centers, N_cubes=N, h_corner=h_corner, w_corner=w_corner, center_hw=np.stack([ch, cw], axis=0),
+                images=images, viewPairs=viewPairs, w_rand=rs.rand(N, viewPairs.shape[0]).astype(np.float32),
+                range_h=np.stack([rs.rand(n_crop) * 200, 200 + rs.rand(n_crop) * 90], axis=1), range_w=np.stack([rs.rand(n_crop) * 300, 300 + rs.rand(n_crop) * 90], axis=1),
+                crop_ch=np.array([5.2, 31.9, 150.5, 299.99, 280.0, 32.0, 100.7]), crop_cw=np.array([390.1, 10.0, 200.49, 399.0, 33.3, 32.0, 64.5]))

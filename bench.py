@@ -5,6 +5,7 @@ view-pair fusion -> float16 -> ray-pool votes) on N B200s of one node.
     python bench.py [--gpus N --steps K --warmup W] [--workload c3|c2|c4] [--mode fp32|exact|fast]
     python bench.py --impl reference ...      the CPU restatement of the reference path on the host cores
     python bench.py --workload post ...       "next" row N4: filter + denoise + adapthresh on the scene's sparse cubes
+    python bench.py --workload simnet ...     "next" row N3: patch crop + similarityNet embedding (early rejection)
 
 A "step" = one batch of the hot loop of main_reconstruct.py:132-162 per GPU.  Workload (default c3,
 BASELINE.json configs[2], the 64^3 configuration the headline target is quoted on; largest single-GPU
@@ -497,19 +498,112 @@ def run_post(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# "next" row N3: early rejection's patch embedding (utils/earlyRejection.py:6-55 on nets/similarityNet.py:23-56)
+SIMNET_FLOP_PER_PATCH = 2.0 * (7.08e6 + 151.0e6 + 75.5e6 + 151.0e6 + 75.5e6 + 2 * 151.0e6 + 75.5e6 + 2 * 151.0e6 + 3 * 37.75e6 + 0.754e6)
+
+
+def run_simnet(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    from tests import util
+    n_patches = 2048
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[k] = str(os.cpu_count() or 1)
+        import torch
+        from oracle import selection_oracle as so
+        from surfacenet_b200 import similarityNet
+        torch.set_num_threads(os.cpu_count() or 1)
+        params = similarityNet.synthetic_params(0)
+        patches = np.random.RandomState(0).randn(64, 3, 64, 64).astype(np.float32) * 50
+        for _ in range(args.warmup):
+            so.patch2embedding_fn(patches, params)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            so.patch2embedding_fn(patches, params)
+        dt = (time.perf_counter() - t0) / args.steps
+        desc = "64 patches of 3x64x64 per step, torch-CPU fp32 VGG-16 embedding"
+        print(json.dumps({"impl": "reference", "metric": "patch embeddings/sec (similarityNet patch2embedding)", "value": 64 / dt, "unit": "patches/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "simnet", "sample": desc},
+                          "cpu_baseline": {"value": 64 / dt, "unit": "patches/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc},
+                          "e2e": {"value": 64 / dt, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+    import torch
+    from surfacenet_b200 import _lib, image, similarityNet
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    net = similarityNet.SimNet(similarityNet.synthetic_params(0))
+    img = torch.from_numpy(util.synth_image(5, 1200, 1600)).cuda()
+    rs = np.random.RandomState(3)
+    ch, cw = rs.rand(n_patches) * 1200, rs.rand(n_patches) * 1600
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step():
+        return net.patch2embedding(image.crop_preprocessed_patches_device(img, ch, cw, 64, util.MEAN_BGR))
+
+    for _ in range(args.warmup):
+        step(); flush.fill_(1)
+    torch.cuda.synchronize()
+    _lib.lib.sn_launch_count_reset()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    t0 = time.time()
+    for a, b in evs:
+        a.record(); out = step(); b.record(); flush.fill_(1)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.window(t0, t1); sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    launches = int(_lib.lib.sn_launch_count()) // args.steps
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        emb = step().cpu().numpy()                                  # e2e: centres up, embeddings back
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    tf = SIMNET_FLOP_PER_PATCH * n_patches / (ms * 1e-3) / 1e12
+    fma_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12
+    line = {"metric": "patch embeddings/sec (similarityNet patch2embedding)", "value": n_patches / (ms * 1e-3), "unit": "patches/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "simnet: %d patches of 3x64x64 cropped from a 1200x1600 image per step (crop + VGG-16 embedding)" % n_patches,
+                       "l2": "256 MiB flush write between timed steps"},
+            "e2e": {"value": n_patches / (ms_e2e * 1e-3), "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n_patches * 16,
+                    "d2h_bytes_per_step": n_patches * 128 * 4},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "cuda-core fp32 FMA (not a tensor-core kernel)", "kernel": "conv2d3x3_kernel x13 (whole embedding)", "achieved": tf,
+                         "peak": fma_peak, "unit": "TFLOP/s", "frac": tf / fma_peak, "traffic": None,
+                         "peak_source": "148 SMs x 128 FMA lanes x 2 x measured SM clock", "flop_per_patch": SIMNET_FLOP_PER_PATCH}}
+    if not args.no_cpu_baseline:
+        import torch as _t
+        from oracle import selection_oracle as so
+        _t.set_num_threads(os.cpu_count() or 1)
+        params = similarityNet.synthetic_params(0)
+        pp = np.random.RandomState(0).randn(64, 3, 64, 64).astype(np.float32) * 50
+        so.patch2embedding_fn(pp[:8], params)
+        t0 = time.perf_counter(); so.patch2embedding_fn(pp, params); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 64 / dt, "unit": "patches/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "64 patches, torch-CPU fp32 VGG-16 embedding (%.2f s)" % dt}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["post"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["post", "simnet"])
     ap.add_argument("--mode", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "post":
         return run_post(args)
+    if args.workload == "simnet":
+        return run_simnet(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)

@@ -54,3 +54,33 @@ def viewPairAngles_wrt_pts(cameraTs, pts_xyz, viewPairs=None, device_out=False):
     _lib.check(_lib.lib.sn_viewpair_angles(_lib.ptr(cam), _lib.ptr(pts), cam.shape[0], pts.shape[0], _lib.ptr(vp), vp.shape[0],
                                            1 if dt == np.float64 else 0, _lib.ptr(out), _lib.stream_ptr()))
     return out if device_out else out.cpu().numpy()
+
+
+def __cameraP2T__(cameraPO):
+    """utils/camera.py:88-100: camera centre in world coordinates from a (3,4) projection matrix (host; four 3x3 determinants)."""
+    cameraPO = np.asarray(cameraPO)
+    homo4D = np.array([np.linalg.det(cameraPO[:, [1, 2, 3]]), -1 * np.linalg.det(cameraPO[:, [0, 2, 3]]),
+                       np.linalg.det(cameraPO[:, [0, 1, 3]]), -1 * np.linalg.det(cameraPO[:, [0, 1, 2]])])
+    return homo4D[:3] / homo4D[3]
+
+
+def cameraPs2Ts(cameraPOs):
+    """utils/camera.py:103-120."""
+    Ts = [__cameraP2T__(P) for P in cameraPOs]
+    return Ts if type(cameraPOs) is list else np.stack(Ts)
+
+
+def perspectiveProj_cubesCorner(projection_M, cube_xyz_min, cube_D_mm, return_int_hw=True, return_depth=False):
+    """utils/camera.py:186-250: projections of the 8 corners of every cube -> img_h, img_w (N_Ms, N_pts, 8) (GPU projection)."""
+    projection_M, cube_xyz_min = np.asarray(projection_M), np.asarray(cube_xyz_min)
+    if projection_M.shape[-2:] != (3, 4):
+        raise ValueError("perspectiveProj needs projection_M with shape (3,4), however got {}".format(projection_M.shape))
+    if cube_xyz_min.ndim == 1:
+        cube_xyz_min = cube_xyz_min[None, :]
+    if cube_xyz_min.ndim != 2 or cube_xyz_min.shape[1] != 3:
+        raise ValueError("perspectiveProj needs cube_xyz_min with shape (3,) or (N_pts, 3), however got {}".format(cube_xyz_min.shape))
+    N_pts = cube_xyz_min.shape[0]
+    cubeCorner_shift = np.indices((2, 2, 2)).reshape((3, -1)).T[None, :, :] * cube_D_mm
+    cubeCorner = cube_xyz_min[:, None, :] + cubeCorner_shift
+    img_h, img_w = perspectiveProj(projection_M=projection_M, xyz_3D=cubeCorner.reshape((N_pts * 8, 3)), return_int_hw=return_int_hw)
+    return img_h.reshape((-1, N_pts, 8)), img_w.reshape((-1, N_pts, 8))

@@ -81,3 +81,56 @@ def finish(result, npz_path=None, ply_path=None, tau=TAU, gamma=GAMMA, cube_D=64
     if npz_path is not None:
         sparseCubes.save_sparseCubes(npz_path, *result)
     return masks, denoised
+
+
+def reconstruction(images_list, cameraPOs_np, BB, resol, N_viewPairs4inference, surfacenet_params, similnet_params, outputFolder=None,
+                   cube_D=64, mode="exact", weighted_fusion=True, batch_size=16, min_prob=MIN_PROB, tau=TAU, gamma=GAMMA,
+                   cube_overlapping_ratio=0.5, patchSize=64, batchSize_patch2embedding=1024, batchSize_pair=1 << 20, model="model",
+                   rank=0, world_size=1):
+    """main_reconstruct.reconstruction (main_reconstruct.py:28-183) from in-memory inputs (the reference reads `images_list`,
+    `cameraPOs_np` and BB from files at :49-50 and params.load_modelSpecific_params): cube grid -> early rejection (similarityNet patch
+    embeddings, pair dissimilarity) -> view-pair selection -> SurfaceNet inference on the fused sparse path -> fixed-threshold mask,
+    cross-cube denoising, PLY + NPZ.  Every stage runs on the GPU drop-ins of this package.
+    -> "Empty!" or dict(npz_path, ply_path, result=(the seven sparse-list items), vxl_mask_list, vxl_maskDenoised_list, validCubes,
+                        viewPairs4Reconstr, w_viewPairs4Reconstr)"""
+    import os
+    from . import SurfaceNet, camera, earlyRejection, similarityNet, viewPairSelection
+    from .device import DeviceScene
+    from .utils import k_combination_np
+    from .weights import MEAN_PATCHES_BGR
+    N = int(N_viewPairs4inference)
+    Dc = CUBE_DCENTER.get(int(cube_D), int(cube_D))
+    cameraPOs_np = np.asarray(cameraPOs_np, dtype=np.float64)
+    cameraTs_np = camera.cameraPs2Ts(cameraPOs_np)                                                        # :51
+    cubes_param_np, cube_D_mm = initialize_cubes(resol, cube_D, Dc, cube_overlapping_ratio, BB)            # :53-55
+    img_h_corner, img_w_corner = camera.perspectiveProj_cubesCorner(cameraPOs_np, cubes_param_np['xyz'], cube_D_mm, return_int_hw=False)
+    centers = cubes_param_np['xyz'] + cube_D_mm / 2
+    img_h_center, img_w_center = camera.perspectiveProj(cameraPOs_np, centers, return_int_hw=False)        # :63-65
+    N_views, N_cubes = img_h_corner.shape[:2]
+    patch2embedding_fn, embeddingPair2simil_fn = similarityNet.similarityNet_inference(similnet_params, (patchSize, patchSize))   # :70
+    viewPair_relativeImpt_fn, nViewPair_SurfaceNet_fn = SurfaceNet.SurfaceNet_inference(N, surfacenet_params, mode=mode)       # :72
+    viewPairs = k_combination_np(range(N_views), k=2)                                                       # :80
+    emb, inScope = earlyRejection.patch2embedding(images_list, img_h_corner, img_w_corner, patch2embedding_fn, MEAN_PATCHES_BGR, N_cubes,
+                                                  N_views, similarityNet.D_EMBEDDING, patchSize=patchSize, batchSize=batchSize_patch2embedding,
+                                                  cubeCenter_hw=np.stack([img_h_center, img_w_center], axis=0))            # :83-88
+    dissimilarity = earlyRejection.embeddingPairs2simil(emb, N_views, inScope, embeddingPair2simil_fn, batchSize_pair, viewPairs)   # :90-95
+    validCubes = earlyRejection.selectFromSimilarity(dissimilarity, N)                                      # :96
+    if int(validCubes.sum()) == 0:
+        return "Empty!"
+    pairs, w = viewPairSelection.viewPairSelection(cameraTs_np, emb, dissimilarity, validCubes, centers, viewPair_relativeImpt_fn,
+                                                   batchSize_pair, N, viewPairs)                            # :104-113
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    if not weighted_fusion:
+        w[:] = 1.0 / N                                                                                      # :115-116
+    hot = HotPath(nViewPair_SurfaceNet_fn.net, DeviceScene(cameraPOs_np, images_list), mode=mode, min_prob=min_prob)
+    res = reconstruct_cubes(hot, cubes_param_np[validCubes], pairs, w, cube_D, Dc, batch_size=batch_size, rank=rank, world_size=world_size)
+    if res == "Empty!":
+        return res
+    npz = ply = None
+    if outputFolder is not None:
+        os.makedirs(outputFolder, exist_ok=True)
+        ply = os.path.join(outputFolder, 'fixThresh_tau{:.3}_gamma{:.3}.ply'.format(tau, gamma))           # :169
+        npz = os.path.join(outputFolder, 'model{}-{}views.npz'.format(model, N_views))                      # :180
+    masks, denoised = finish(res, npz_path=npz, ply_path=ply, tau=tau, gamma=gamma, cube_D=cube_D)
+    return dict(npz_path=npz, ply_path=ply, result=res, vxl_mask_list=masks, vxl_maskDenoised_list=denoised, validCubes=validCubes,
+                viewPairs4Reconstr=pairs, w_viewPairs4Reconstr=w)

@@ -29,6 +29,7 @@ D_VIEWPAIR_FEATURE = 258        # params.py:94
 SIMILNET_HIDDEN = 100           # params.py:95
 N_ARRAYS = 105
 MEAN_CVC_RGBRGB = np.asarray([123.68, 116.779, 103.939, 123.68, 116.779, 103.939], dtype=np.float32)  # params.py:129
+MEAN_PATCHES_BGR = np.asarray([103.939, 116.779, 123.68], dtype=np.float32)                           # params.py:130
 
 
 def unit_index():

@@ -153,3 +153,32 @@ def test_end_to_end_early_rejection_and_selection_vs_oracle(case, g):
     fo = lambda f, n_samples_perGroup: surfacenet_oracle.viewPair_relativeImpt_fn(f, params, n_samples_perGroup)
     selo, wo = so.viewPairSelection(cT, emb_o, dis_o, valid, case["centers"].astype(np.float32), fo, 100, 2, vp)
     assert np.abs(w - wo).max() <= 1e-3 and selp.shape == selo.shape == (case["N_cubes"], 2, 2)
+
+
+def test_whole_scene_reconstruction_runs_end_to_end(tmp_path, cams):
+    """main_reconstruct.reconstruction from arrays: cube grid -> early rejection -> view-pair selection -> SurfaceNet inference ->
+    thresholding + denoising -> PLY / NPZ -> adapthresh, every stage on the GPU drop-ins (each stage has its own parity test;
+    here the chain is checked for consistency)."""
+    from surfacenet_b200 import adapthresh, reconstruct, similarityNet, sparseCubes, weights
+    views = [3, 8, 15, 22, 30]
+    images = [util.synth_image(200 + v, 1200, 1600) for v in views]
+    P = cams[views]
+    BB = np.array([[-10.0, 15.0], [-20.0, 5.0], [620.0, 645.0]])
+    # permissive similarity head (sigmoid(-0.02 d - 0.4) in (0.1, 0.5) for most pairs) so that cubes survive early rejection
+    sp = similarityNet.synthetic_params(0)
+    sp[28] = np.array([[-0.02]], np.float32); sp[29] = np.array([-0.4], np.float32)
+    out = reconstruct.reconstruction(images, P, BB, np.float32(0.4), 2, weights.synthetic_params(0), sp, outputFolder=str(tmp_path),
+                                     cube_D=32, mode="exact", batch_size=8, tau=0.5, gamma=0.0, model="synth")
+    assert out != "Empty!"
+    n_valid = int(out["validCubes"].sum())
+    assert n_valid > 0 and out["viewPairs4Reconstr"].shape == (n_valid, 2, 2) and out["w_viewPairs4Reconstr"].shape == (n_valid, 2)
+    assert np.all(out["viewPairs4Reconstr"] < len(views)) and np.allclose(out["w_viewPairs4Reconstr"].sum(axis=1) <= 1.0 + 1e-5, True)
+    pl, rl, il, vl, cube_ijk, param, vp = out["result"]
+    assert len(pl) == len(il) == cube_ijk.shape[0] > 0 and il[0].max() < 26
+    back = sparseCubes.load_sparseCubes(out["npz_path"])
+    assert all(np.array_equal(a, b) for a, b in zip(back[0], pl))
+    xyz, _ = util.read_ply(out["ply_path"])
+    assert xyz.shape[0] == int(sum(d.sum() for d in out["vxl_maskDenoised_list"]))
+    last = adapthresh.adapthresh(save_result_fld=str(tmp_path), N_refine_iter=2, D_cube=26, init_probThresh=0.5, min_probThresh=0.5,
+                                 max_probThresh=0.9, rayPool_thresh=0, beta=6, gamma=0.8, npz_file=out["npz_path"], RGB_visual_ply=False)
+    assert os.path.exists(last) and last.endswith("iter1.ply")

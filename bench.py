@@ -351,6 +351,14 @@ def post_step_oracle(sc, iters):
     post.adapthresh_core(sc["pred_list"], sc["ijk_list"], sc["votes_list"], sc["cube_ijk"], iters, D, 0.5, 0.5, 0.9, 8, 6)
 
 
+def post_traffic(dom):
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "ncu_summary.json")))["post"]
+        return d["denoise_call"]["dram_bytes_per_call"] if dom == "denoise" else None
+    except Exception:
+        return None
+
+
 def run_post(args):
     import numpy as np
     rank = int(os.environ.get("RANK", "0"))
@@ -480,7 +488,7 @@ def run_post(args):
                         "what": "adapthresh_lists: per-cube numpy lists in, per-iteration masks + denoised masks out (wall clock)"},
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "the %s C-ABI call (%d launches)" % (dom, {"denoise": 11, "adapthresh_iter": 9}[dom]),
-                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": post_traffic(dom),
                              "peak_source": peak_src, "bytes_per_call": bytes_call[dom], "ms_per_call": dom_ms,
                              "calls_ms_per_step": {k: parts[k] for k in parts}, "calls_per_step": n_calls}}
         if world == 1 and not args.no_cpu_baseline:

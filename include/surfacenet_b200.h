@@ -260,7 +260,7 @@ int sn_viewpair_angles(const void* cameraTs_dev, const void* pts_dev, int n_view
 int sn_viewpair_features(const float* emb_dev, const int32_t* viewpairs_dev, const float* dissim_dev, const void* theta_dev,
                          int theta_is_f64, int64_t n_cubes, int n_views, int n_pairs, int D_embedding, float* out_dev, void* stream);
 /* utils/viewPairSelection.py:36  w.argsort(axis=1)[:, -N:]: per row the indices of the N largest values, ascending by value
- *   (equal values in index order; numpy leaves ties unspecified).  w_dev (n_rows, n) f64, n <= 4096 -> idx_out_dev (n_rows, N) i32 */
+ *   (equal values in index order; numpy leaves ties unspecified).  w_dev (n_rows, n) f64, n <= 8192 -> idx_out_dev (n_rows, N) i32 */
 int sn_topn_rows(const double* w_dev, int64_t n_rows, int n, int N, int32_t* idx_out_dev, void* stream);
 /* utils/earlyRejection.py:82-93  selectFromSimilarity: ((d < 0.5) & (d > 0.1)).sum(axis=1) >= N -> out_dev (n_cubes) u8 */
 int sn_select_from_similarity(const float* dissim_dev, int64_t n_cubes, int n_pairs, int N, uint8_t* out_dev, void* stream);

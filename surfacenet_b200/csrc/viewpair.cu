@@ -74,8 +74,8 @@ __global__ void vp_features_kernel(const float* __restrict__ emb, const int32_t*
 }
 
 // per row: indices of the N largest values in ascending value order = argsort(row)[-N:]; equal values keep index order
-// (numpy's default sort leaves ties unspecified).  Bitonic sort of (value, index) in shared memory, n <= 4096.
-constexpr int TOPN_MAX = 4096;
+// (numpy's default sort leaves ties unspecified).  Bitonic sort of (value, index) in shared memory, n <= 8192.
+constexpr int TOPN_MAX = 8192;
 __global__ void __launch_bounds__(1024)
 topn_rows_kernel(const double* __restrict__ w, int n, int n_pad, int N, int32_t* __restrict__ idx_out) {
     extern __shared__ unsigned char smem_raw[];

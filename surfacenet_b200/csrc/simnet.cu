@@ -3,7 +3,7 @@
 //   patch (3,64,64) BGR - mean -> 13 x [3x3 conv pad 1 + bias + ReLU] with 2x2 max-pools (VGG-16 widths 64..512)
 //   -> concat[flatten(pool5), centre 2x2 crops of pool1..pool4] (5888) -> L2 normalise -> Dense 128        similarityNet.py:28-56
 //   pair: ||e1 - e2||_2 -> Dense(1) -> sigmoid                                                              similarityNet.py:72-77
-// fp32 on the CUDA cores (FMA-bound direct convolution, weights broadcast from shared memory); this net runs once per
+// fp32 on the CUDA cores (FMA-bound direct convolution, 4 pixels x 32 channels per thread, weights broadcast from shared memory); this net runs once per
 // (cube, view) before the hot loop and is not on the north-star path, so it gets the simple exact-precision kernel.
 #include "common.cuh"
 #include <algorithm>
@@ -12,7 +12,7 @@
 
 struct sn_simnet {
     int patch;
-    float* conv_w[13];      // [Cout/64][Cin][9][64]
+    float* conv_w[13];      // [Cout/32][Cin][9][32]
     float* conv_b[13];
     float* dense_w;         // (5888, 128)
     float* dense_b;         // (128)
@@ -24,60 +24,80 @@ namespace sn {
 static const int SIM_CIN[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
 static const int SIM_COUT[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
 static const int SIM_POOL_AFTER[13] = {0, 1, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1};
-constexpr int SIM_COT = 64, SIM_CI = 8, SIM_THREADS = 256, SIM_E = 128, SIM_CONCAT = 5888;
+constexpr int SIM_COT = 32, SIM_PX = 4, SIM_CI = 8, SIM_THREADS = 128, SIM_E = 128, SIM_CONCAT = 5888;
 
 // out[n,co,y,x] = relu(b[co] + sum_{ci,ky,kx} in[n,ci,y+ky-1,x+kx-1] * W[co,ci,ky,kx])   (cross-correlation: Conv2DDNNLayer, flip_filters=False)
+// One thread = SIM_PX consecutive pixels of a row x SIM_COT output channels (128 accumulators): every weight float4 fetched
+// from shared memory (a broadcast) feeds 4 pixels x 4 channels = 16 FMAs and the 3 x 6 input window of the 4 pixels is loaded
+// once per input channel, so the FMA pipe -- not the shared-memory pipe -- is the limiter.
 __global__ void __launch_bounds__(SIM_THREADS)
 conv2d3x3_kernel(const float* __restrict__ in, const float* __restrict__ wt, const float* __restrict__ bias, float* __restrict__ out,
                  int64_t n_img, int Cin, int Cout, int H, int W) {
-    __shared__ float s_w[SIM_CI][9][SIM_COT];
-    const int64_t pix = (int64_t)blockIdx.x * SIM_THREADS + threadIdx.x;
-    const int64_t total = n_img * H * W;
-    const bool live = pix < total;
-    const int x = live ? (int)(pix % W) : 0, y = live ? (int)((pix / W) % H) : 0;
-    const int64_t n = live ? pix / ((int64_t)W * H) : 0;
+    __shared__ __align__(16) float s_w[SIM_CI][9][SIM_COT];
+    const int Wq = W / SIM_PX;                                       // W is a multiple of 4 for every VGG map (64 ... 4)
+    const int64_t quad = (int64_t)blockIdx.x * SIM_THREADS + threadIdx.x;
+    const int64_t total = n_img * H * Wq;
+    const bool live = quad < total;
+    const int x0 = live ? (int)(quad % Wq) * SIM_PX : 0, y = live ? (int)((quad / Wq) % H) : 0;
+    const int64_t n = live ? quad / ((int64_t)Wq * H) : 0;
     const int cog = blockIdx.y;
-    float acc[SIM_COT];
+    float acc[SIM_PX][SIM_COT];
 #pragma unroll
-    for (int c = 0; c < SIM_COT; ++c) acc[c] = 0.f;
+    for (int p = 0; p < SIM_PX; ++p)
+#pragma unroll
+        for (int c = 0; c < SIM_COT; ++c) acc[p][c] = 0.f;
     const float* in_n = in + n * Cin * (int64_t)H * W;
     const float* wt_g = wt + (int64_t)cog * Cin * 9 * SIM_COT;
-    bool ok[9];
-    int offs[9];
+    bool okr[3], okl, okr_edge;                                      // rows y-1..y+1 inside?  columns x0-1 / x0+4 inside?
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-        ok[t] = live && yy >= 0 && yy < H && xx >= 0 && xx < W;
-        offs[t] = yy * W + xx;
-    }
+    for (int r = 0; r < 3; ++r) okr[r] = live && (y + r - 1) >= 0 && (y + r - 1) < H;
+    okl = x0 > 0; okr_edge = x0 + SIM_PX < W;
     for (int ci0 = 0; ci0 < Cin; ci0 += SIM_CI) {
         const int nci = min(SIM_CI, Cin - ci0);
         __syncthreads();
         for (int i = threadIdx.x; i < nci * 9 * SIM_COT; i += SIM_THREADS) (&s_w[0][0][0])[i] = wt_g[(int64_t)ci0 * 9 * SIM_COT + i];
         __syncthreads();
         for (int ci = 0; ci < nci; ++ci) {
-            const float* p = in_n + (int64_t)(ci0 + ci) * H * W;
-            float xv[9];
+            const float* p = in_n + (int64_t)(ci0 + ci) * H * W + (int64_t)y * W + x0;
+            float xv[3][SIM_PX + 2];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) xv[t] = ok[t] ? __ldg(p + offs[t]) : 0.f;
+            for (int r = 0; r < 3; ++r) {
+                const float* pr = p + (r - 1) * W;
+                float4 mid = make_float4(0.f, 0.f, 0.f, 0.f);
+                float lft = 0.f, rgt = 0.f;
+                if (okr[r]) {
+                    mid = __ldg(reinterpret_cast<const float4*>(pr));
+                    if (okl) lft = __ldg(pr - 1);
+                    if (okr_edge) rgt = __ldg(pr + SIM_PX);
+                }
+                xv[r][0] = lft; xv[r][1] = mid.x; xv[r][2] = mid.y; xv[r][3] = mid.z; xv[r][4] = mid.w; xv[r][5] = rgt;
+            }
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const float4* w4 = reinterpret_cast<const float4*>(&s_w[ci][t][0]);
 #pragma unroll
                 for (int c = 0; c < SIM_COT / 4; ++c) {
                     const float4 w = w4[c];
-                    acc[4 * c + 0] = fmaf(xv[t], w.x, acc[4 * c + 0]);
-                    acc[4 * c + 1] = fmaf(xv[t], w.y, acc[4 * c + 1]);
-                    acc[4 * c + 2] = fmaf(xv[t], w.z, acc[4 * c + 2]);
-                    acc[4 * c + 3] = fmaf(xv[t], w.w, acc[4 * c + 3]);
+#pragma unroll
+                    for (int q = 0; q < SIM_PX; ++q) {
+                        const float xq = xv[t / 3][q + t % 3];
+                        acc[q][4 * c + 0] = fmaf(xq, w.x, acc[q][4 * c + 0]);
+                        acc[q][4 * c + 1] = fmaf(xq, w.y, acc[q][4 * c + 1]);
+                        acc[q][4 * c + 2] = fmaf(xq, w.z, acc[q][4 * c + 2]);
+                        acc[q][4 * c + 3] = fmaf(xq, w.w, acc[q][4 * c + 3]);
+                    }
                 }
             }
         }
     }
     if (!live) return;
-    float* o = out + (n * Cout + (int64_t)cog * SIM_COT) * H * W + (int64_t)y * W + x;
+    float* o = out + (n * Cout + (int64_t)cog * SIM_COT) * H * W + (int64_t)y * W + x0;
 #pragma unroll
-    for (int c = 0; c < SIM_COT; ++c) o[(int64_t)c * H * W] = fmaxf(acc[c] + __ldg(bias + cog * SIM_COT + c), 0.f);
+    for (int c = 0; c < SIM_COT; ++c) {
+        const float b = __ldg(bias + cog * SIM_COT + c);
+        *reinterpret_cast<float4*>(o + (int64_t)c * H * W) = make_float4(fmaxf(acc[0][c] + b, 0.f), fmaxf(acc[1][c] + b, 0.f),
+                                                                         fmaxf(acc[2][c] + b, 0.f), fmaxf(acc[3][c] + b, 0.f));
+    }
 }
 
 __global__ void maxpool2d_kernel(const float* __restrict__ in, int64_t total_out, int H, int W, float* __restrict__ out) {
@@ -221,8 +241,8 @@ extern "C" int sn_simnet_patch2embedding(const sn_simnet* h, const float* patche
     for (int l = 0; l < 13; ++l) {
         const int Cin = SIM_CIN[l], Cout = SIM_COUT[l];
         float* dst = buf[which];
-        const int64_t pix = n_patches * S * S;
-        conv2d3x3_kernel<<<dim3((unsigned)cdiv(pix, SIM_THREADS), Cout / SIM_COT), SIM_THREADS, 0, st>>>(cur, h->conv_w[l], h->conv_b[l], dst,
+        const int64_t quads = n_patches * S * (S / SIM_PX);
+        conv2d3x3_kernel<<<dim3((unsigned)cdiv(quads, SIM_THREADS), Cout / SIM_COT), SIM_THREADS, 0, st>>>(cur, h->conv_w[l], h->conv_b[l], dst,
                                                                                                        n_patches, Cin, Cout, S, S);
         SN_LAUNCHED();
         cur = dst; which ^= 1;

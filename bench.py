@@ -316,7 +316,8 @@ def run_gpu(args, wl):
                          "kernel_share_of_step": ms_u[dom] / args.steps / ms_dev,
                          "all_conv_units": {"launches_per_step": conv_launches // args.steps, "tflops": conv_tflops, "frac": conv_tflops / tc_peak,
                                             "share_of_step": conv_ms / args.steps / ms_dev},
-                         "exact_mode_ceiling_frac": (1.0 / 3.0) * (100.0 / 112.0) ** 2 if mode in ("exact", "tc_exact") else None,
+                         # merge_conv2, exact: 3 products; columns 208 + 112 per (block, tap) for 3 x 100 real ones; K elements 6 x 27 x 16 + 18 x 16 for 27 x 100
+                         "exact_mode_ceiling_frac": (1.0 / 3.0) * (300.0 / 320.0) * (2700.0 / 2880.0) if mode in ("exact", "tc_exact") else None,
                          "per_unit": per_unit},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -117,6 +117,10 @@ struct ConvTcParams {
     int a_prec_bytes;               // bytes of one precision plane of one A stage = PW*HH*HD*32
     int tiles_w, tiles_h, tiles_d;
     int n_ntiles, nt_size[TC_MAX_NT], nt_off[TC_MAX_NT];
+    int pair_last, nv_last;         // last 16-channel block holds <= 8 real channels: its MMAs take the channel group at TWO taps as the two K halves
+                                    // (LBO = distance of the taps in the halo tile), nv_last = 2*K*K tap pairs instead of K^3 taps
+    int nt_nc[TC_MAX_NT];           // exact mode: column of the correction accumulator = rows of W_hi in the stage = real channels of the tile
+                                    // rounded up to 8 (<= nt_size); the [W_hi ; W_lo] operand then has 2*nt_nc rows instead of 2*nt_size
     long long nt_woff[TC_MAX_NT];   // byte offset of the N-tile's weights
     const unsigned char* weights;   // [ntile][cblk][tap][kg 2][prec][N/8][8 n][8 k] fp16
     const float* scale;             // folded BatchNorm (x 2^-k of the weight pre-scaling), zero for padded channels
@@ -199,6 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
     uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + NB;
     uint64_t* acc_full = bars + 4 + 2 * NB, *acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint32_t* pair_tbl = tmem_slot + 4;                               // [32] tap-pair descriptors of the last channel block (pair_last)
     const int pad = p.dil * (p.K / 2);
     const int nbuf = p.nbuf;
     const uint32_t buf_cols = (uint32_t)(AD * P * Nmax);
@@ -244,11 +249,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
         }
     } else if (warp == 1) {
         // ===== B producer: the (channel block, tap) weight tile, already in canonical layout in HBM =====
-        const int total = p.n_cblk * p.taps / p.TPS;
+        const int total = ((p.n_cblk - 1) * p.taps + (p.pair_last ? p.nv_last : p.taps)) / p.TPS;
         int s = 0; uint32_t ph = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const TileCoord c = tile_coord<AD>(p, t);
-            const uint32_t stage_bytes = (uint32_t)p.nt_size[c.nt] * 32 * P * p.TPS;
+            const uint32_t stage_bytes = (uint32_t)(P == 2 ? 2 * p.nt_nc[c.nt] : p.nt_size[c.nt]) * 32 * p.TPS;
             const unsigned char* wsrc = p.weights + p.nt_woff[c.nt];
             for (int it = 0; it < total; ++it) {
                 mbar_wait(&b_empty[s], ph ^ 1);
@@ -275,14 +280,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
         const uint32_t b_slot16 = b_slot_bytes >> 4;
         const uint32_t plane16 = (uint32_t)(p.HH * p.PW), row16 = (uint32_t)p.PW;
         const uint32_t dil = (uint32_t)p.dil;
+        if (p.pair_last) {                                                   // virtual tap v -> taps (2v, 2v+1); beyond K^3 the weights are zero
+            const int lane = threadIdx.x & 31, K2 = p.K * p.K;
+            if (lane < p.nv_last) {
+                const int ta = min(2 * lane, p.taps - 1), tb = min(2 * lane + 1, p.taps - 1);
+                const uint32_t oa = ((ta / K2) * plane16 + ((ta / p.K) % p.K) * row16 + (ta % p.K)) * dil;
+                const uint32_t ob = ((tb / K2) * plane16 + ((tb / p.K) % p.K) * row16 + (tb % p.K)) * dil;
+                pair_tbl[lane] = oa | ((ob - oa) << 16);
+            }
+            __syncwarp();
+        }
         int sb = 0; uint32_t phb = 0, ia = 0, j = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
             const TileCoord c = tile_coord<AD>(p, t);
             const int N = p.nt_size[c.nt];
-            const uint32_t idesc1 = (1u << 4) | ((uint32_t)((P * N) >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, M=128
+            const int Nc = p.nt_nc[c.nt];                                    // exact: rows of W_hi before W_lo = corr column offset
+            const int R = (P == 2) ? 2 * Nc : N;                             // rows of the stage per K half
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(R >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major, M=128
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t b_lbo = (uint32_t)(P * N) << 16;                  // one K half of the stage: P*N rows of 16 B
-            const uint32_t tapB16 = (uint32_t)(2 * P * N);                   // one tap of the slot = 2 K halves
+            const uint32_t b_lbo = (uint32_t)R << 16;                        // one K half of the stage: R rows of 16 B
+            const uint32_t tapB16 = (uint32_t)(2 * R);                       // one tap of the slot = 2 K halves
             const uint32_t buf = (nbuf == 2) ? (j & 1) : 0;
             const uint32_t use = (nbuf == 2) ? (j >> 1) : j;                 // how often this accumulator set was used before
             const uint32_t dbase = tmem_base + buf * buf_cols;
@@ -294,7 +311,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                 mbar_wait(&a_full[sa], (ia >> 1) & 1);
                 tc_fence_after();
                 const uint32_t a_lo32 = (smA16 + sa * a_stage16) | a_lbo;
-                for (int kd = 0; kd < p.K; ++kd)
+                const bool paired = p.pair_last && cb == p.n_cblk - 1;     // tap pairs as K halves (see ConvTcParams::pair_last)
+                const int n_kd = paired ? p.nv_last / (p.K * p.K) : p.K;
+                for (int kd = 0; kd < n_kd; ++kd)
                     for (int t0 = 0; t0 < p.K * p.K; t0 += p.TPS) {          // slot = TPS consecutive (kh, kw) taps of this kd
                         mbar_wait(&b_full[sb], phb);
                         tc_fence_after();
@@ -302,7 +321,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                             uint64_t db = ((uint64_t)b_hi32 << 32) | ((smB16 + sb * b_slot16) | b_lbo);
                             int kh = t0 / p.K, kw = t0 - kh * p.K;
                             for (int kk = 0; kk < p.TPS; ++kk, db += tapB16) {
-                                const uint32_t a_tap = a_lo32 + (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
+                                uint32_t a_tap = a_lo32 + (kd * dil * plane16) + (kh * dil * row16) + kw * dil;
+                                if (paired) a_tap = (smA16 + sa * a_stage16) + pair_tbl[kd * p.K * p.K + t0 + kk];   // start offset | LBO << 16
 #pragma unroll
                                 for (int a = 0; a < AD; ++a) {
                                     if (NI == 2 && (a & 1) != me) continue;
@@ -314,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                                     for (int a = 0; a < AD; ++a) {
                                         if (NI == 2 && (a & 1) != me) continue;
                                         const uint64_t da_lo = ((uint64_t)a_hi32 << 32) | (a_tap + a_prec16 + a * plane16);
-                                        tc_mma(dbase + (uint32_t)(a * P * N + N), da_lo, db, idesc2, 1u);
+                                        tc_mma(dbase + (uint32_t)(a * P * N + Nc), da_lo, db, idesc2, 1u);
                                     }
                                 }
                                 acc_flag = 1u;
@@ -342,6 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
             const TileCoord c = tile_coord<AD>(p, t);
             const int N = p.nt_size[c.nt];
+            const int Nc = p.nt_nc[c.nt];
             const int c_base = p.nt_off[c.nt];
             const int h = c.h0 + (m >> 3), w = c.w0 + (m & 7);
             const uint32_t buf = (nbuf == 2) ? (j & 1) : 0;
@@ -364,7 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                     tc_ld16(trow + jc, v);
                     if (P == 2) {
                         uint32_t cc[16];
-                        tc_ld16(trow + (uint32_t)N + jc, cc);
+                        tc_ld16(trow + (uint32_t)Nc + jc, cc);
                         tc_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cc[i]));
@@ -609,12 +630,12 @@ static inline int ew_blocks(long long total) { return (int)std::min<long long>(c
 // host side: weight preparation, tensor maps, launches
 struct TileCfg { int AD, NB, persist, tps; };          // d-planes per CTA, weight-ring depth, CTA scheduling (see conv_tc_launch_cfg)
 struct TcVariant {                                 // [0] exact (P = 2), [1] fast (P = 1): own N tiling and weight image
-    int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0};
+    int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0}, nt_nc[TC_MAX_NT] = {0, 0, 0, 0};
     long long nt_woff[TC_MAX_NT] = {0, 0, 0, 0};
     unsigned char* w = nullptr;
 };
 struct TcUnit {
-    int Cin_pad = 0, Cout_pad = 0, taps = 0;
+    int Cin_pad = 0, Cout_pad = 0, taps = 0, pair_last = 0, nv_last = 0;
     float* side_w = nullptr;                       // for side units with one-N-tile producers: [Cin_pad][16] fp32 (transposed)
     TcVariant v[2];
     float* scale = nullptr;                        // Cout_pad entries, zero for padded channels
@@ -650,6 +671,10 @@ int tc_prepare(Net& net) {
         if (wmax > 0.f) { e = (int)floorf(log2f(1024.f / wmax)); e = std::max(-14, std::min(24, e)); }
         const float wscale = ldexpf(1.f, e), inv = ldexpf(1.f, -e);
         const int n_cblk = tu.Cin_pad / 16;
+        // last channel block with <= 8 real channels (100 -> 96 + 4, 6): pair two taps per MMA instead of multiplying a zero K half
+        static const int env_pair = getenv("SN_TC_KPAIR") ? atoi(getenv("SN_TC_KPAIR")) : 1;
+        tu.pair_last = (env_pair && cu.K == 3 && cu.Cin % 16 >= 1 && cu.Cin % 16 <= 8) ? 1 : 0;
+        tu.nv_last = 2 * cu.K * cu.K;                                   // >= ceil(K^3 / 2) and a multiple of every slot size (1, K, K*K)
         for (int variant = 0; variant < 2; ++variant) {
             TcVariant& tv = tu.v[variant];
             const int P = variant == 0 ? 2 : 1;
@@ -661,28 +686,43 @@ int tc_prepare(Net& net) {
                 const int sz = pad16((int)cdiv(left, tv.n_ntiles - t));
                 tv.nt_size[t] = std::min(sz, left); tv.nt_off[t] = off; off += tv.nt_size[t]; left -= tv.nt_size[t];
             }
+            // exact mode: the W_lo rows follow the W_hi rows of the REAL channels (rounded up to 8), so that the combined operand has
+            // 2*nc rows (100 channels: 208 instead of 224); W_hi alone is still read as nt_size rows (the surplus rows are the first
+            // W_lo rows and land in accumulator columns nobody reads).  SN_TC_TRIM=0 restores nc = nt_size.
+            static const int env_trim = getenv("SN_TC_TRIM") ? atoi(getenv("SN_TC_TRIM")) : 1;
             size_t bytes = 0;
-            for (int t = 0; t < tv.n_ntiles; ++t) { tv.nt_woff[t] = (long long)bytes; bytes += (size_t)n_cblk * K3 * P * tv.nt_size[t] * 32; }
+            for (int t = 0; t < tv.n_ntiles; ++t) {
+                const int real = std::max(0, std::min(tv.nt_size[t], cu.Cout - tv.nt_off[t]));
+                tv.nt_nc[t] = (P == 2 && env_trim) ? std::max((int)align_up(real, 8), (tv.nt_size[t] + 1) / 2) : tv.nt_size[t];
+                if (tv.nt_nc[t] % 8) tv.nt_nc[t] = (int)align_up(tv.nt_nc[t], 8);
+                tv.nt_woff[t] = (long long)bytes;
+                bytes += (size_t)((n_cblk - 1) * K3 + (tu.pair_last ? tu.nv_last : K3)) * (P == 2 ? 2 * tv.nt_nc[t] : tv.nt_size[t]) * 32;
+            }
             std::vector<__half> h(bytes / 2, __float2half_rn(0.f));
             for (int t = 0; t < tv.n_ntiles; ++t) {
                 const int N = tv.nt_size[t];
+                const int Nc = tv.nt_nc[t], R = (P == 2) ? 2 * Nc : N;
                 __half* base = h.data() + tv.nt_woff[t] / 2;
-                for (int cb = 0; cb < n_cblk; ++cb)
-                    for (int tap = 0; tap < K3; ++tap)
+                for (int cb = 0; cb < n_cblk; ++cb) {
+                    const bool paired = tu.pair_last && cb == n_cblk - 1;
+                    for (int tap = 0; tap < (paired ? tu.nv_last : K3); ++tap)            // paired: `tap` is the virtual tap (pair index)
                         for (int nn = 0; nn < N; ++nn)
                             for (int kk = 0; kk < 16; ++kk) {
-                                const int co = tv.nt_off[t] + nn, ci = cb * 16 + kk;
-                                if (co >= cu.Cout || ci >= cu.Cin) continue;
-                                const float wv = cu.h_w[((size_t)co * cu.Cin + ci) * K3 + tap] * wscale;
+                                const int co = tv.nt_off[t] + nn;
+                                const int ci = paired ? cb * 16 + kk % 8 : cb * 16 + kk;      // paired: both K halves are channel group 2*cb
+                                const int rtap = paired ? 2 * tap + kk / 8 : tap;           //         at taps 2v and 2v+1
+                                if (co >= cu.Cout || ci >= cu.Cin || rtap >= K3) continue;
+                                const float wv = cu.h_w[((size_t)co * cu.Cin + ci) * K3 + rtap] * wscale;
                                 const __half hi = __float2half_rn(wv);
                                 const __half lo = __float2half_rn(wv - __half2float(hi));
                                 // stage = [kg = kk/8][prec][ng = nn/8][nn%8][kk%8]: for each K half the N rows of W_hi then of W_lo,
                                 // so that [W_hi ; W_lo] is ONE canonical K-major operand of 2N rows and W_hi alone its first N rows
-                                const size_t stage = ((size_t)cb * K3 + tap) * P * N * 16;
-                                const size_t idx = (size_t)(kk / 8) * P * N * 8 + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (kk % 8);
+                                const size_t stage = ((size_t)cb * K3 + tap) * R * 16;
+                                const size_t idx = (size_t)(kk / 8) * R * 8 + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (kk % 8);
                                 base[stage + idx] = hi;
-                                if (P == 2) base[stage + (size_t)N * 8 + idx] = lo;
+                                if (P == 2) base[stage + (size_t)Nc * 8 + idx] = lo;
                             }
+                }
             }
             SN_CUDA(cudaMalloc((void**)&tv.w, bytes));
             SN_CUDA(cudaMemcpy(tv.w, h.data(), bytes, cudaMemcpyHostToDevice));
@@ -694,7 +734,8 @@ int tc_prepare(Net& net) {
         const double kRzLoss = 0.5 * 0.70 * ldexp(1.0, -23) * 0.5;
         static const int env_comp = getenv("SN_TC_RZCOMP") ? atoi(getenv("SN_TC_RZCOMP")) : 1;
         static const double env_scale = getenv("SN_TC_RZSCALE") ? atof(getenv("SN_TC_RZSCALE")) : 1.0;
-        const float comp = env_comp ? (float)(1.0 + env_scale * kRzLoss * (double)n_cblk * K3) : 1.f;
+        const double n_acc = (double)(n_cblk - 1) * K3 + (tu.pair_last ? (K3 + 1) / 2 : K3);       // accumulating MMAs with non-zero operands
+        const float comp = env_comp ? (float)(1.0 + env_scale * kRzLoss * n_acc) : 1.f;
         std::vector<float> sc(tu.Cout_pad, 0.f), sh(tu.Cout_pad, 0.f);
         for (int c = 0; c < cu.Cout; ++c) { sc[c] = cu.h_scale[c] * inv * comp; sh[c] = cu.h_shift[c]; }
         SN_CUDA(cudaMalloc((void**)&tu.scale, sc.size() * 4));
@@ -772,7 +813,7 @@ static size_t tc_smem_bytes(const ConvUnit& cu, int Nmax, int P, TileCfg c) {
     const int pad = cu.dil * (cu.K / 2);
     const int PW = TC_TW + 2 * pad, HH = TC_TH + 2 * pad;
     const int tps = c.tps == 2 ? cu.K * cu.K : (c.tps == 1 ? cu.K : 1);
-    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P * tps + (8 + 2 * c.NB) * 8 + 16;
+    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P * tps + (8 + 2 * c.NB) * 8 + 16 + 128;
 }
 
 // feasible (d-planes per CTA, weight-ring depth) pairs: <= 512 TMEM columns (P accumulators per plane), <= 227 KB smem.
@@ -821,7 +862,7 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     const TcVariant& tv = tu.v[(a.P == 2) ? 0 : 1];
     const int P = a.P, S = a.S;
     ConvTcParams p{};
-    p.S = S; p.n_pc = a.n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.n_cblk = tu.Cin_pad / 16; p.cg_in = tu.Cin_pad / 8;
+    p.S = S; p.n_pc = a.n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.pair_last = tu.pair_last; p.nv_last = tu.nv_last; p.n_cblk = tu.Cin_pad / 16; p.cg_in = tu.Cin_pad / 8;
     p.NB = cfg.NB; p.TPS = cfg.tps == 2 ? cu.K * cu.K : (cfg.tps == 1 ? cu.K : 1);
     const int AD = cfg.AD;
     const int pad = cu.dil * (cu.K / 2);
@@ -830,7 +871,7 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     p.tiles_w = (int)cdiv(S, TC_TW); p.tiles_h = (int)cdiv(S, TC_TH); p.tiles_d = (int)cdiv(S, AD);
     p.n_ntiles = tv.n_ntiles;
     int Nmax = 0;
-    for (int t = 0; t < TC_MAX_NT; ++t) { p.nt_size[t] = tv.nt_size[t]; p.nt_off[t] = tv.nt_off[t]; p.nt_woff[t] = tv.nt_woff[t]; Nmax = std::max(Nmax, tv.nt_size[t]); }
+    for (int t = 0; t < TC_MAX_NT; ++t) { p.nt_size[t] = tv.nt_size[t]; p.nt_off[t] = tv.nt_off[t]; p.nt_woff[t] = tv.nt_woff[t]; p.nt_nc[t] = tv.nt_nc[t]; Nmax = std::max(Nmax, tv.nt_size[t]); }
     p.weights = tv.w; p.scale = tu.scale; p.shift = tu.shift; p.act = cu.act; p.epi = a.epi;
     p.out = a.out; p.cg_out_total = a.cg_out_total; p.cg_out_off = a.cg_out_off;
     p.w3 = st->w3; p.scale3 = st->scale3; p.shift3 = st->shift3; p.c3 = a.net->units[U_MERGE3].Cin; p.prob_out = a.prob_out;

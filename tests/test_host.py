@@ -256,3 +256,14 @@ def test_post_workspace_and_symbols():
     assert _lib.lib.sn_sparse_post_workspace_bytes(24420, 50000000, 52) > 24420 * (52 ** 3 // 32) * 8
     assert _lib.lib.sn_sparse_post_workspace_bytes(4, 100, 0) == -1 and _lib.lib.sn_sparse_post_workspace_bytes(4, 100, 257) == -1
     assert _lib.lib.sn_sparse_post_workspace_bytes(0, 0, 1) > 0
+
+
+def test_bench_simnet_reference_arm_json():
+    """bench.py --workload simnet --impl reference: one JSON line with the contract keys (torch-CPU VGG-16 embedding, no GPU)."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", "simnet", "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "patches/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0

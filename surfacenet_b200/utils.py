@@ -37,3 +37,41 @@ def k_combination_np(iterable, k=2):
     """utils/utils.py:233-256: all k-combinations of `iterable` as the rows of an array (host index bookkeeping)."""
     import itertools
     return np.asarray(list(itertools.combinations(iterable, k)))
+
+
+# ---- host-side batching helpers of utils/utils.py:45-230 (index bookkeeping used by main_reconstruct.py:123 and the callers of
+# the similarityNet functions); same names, same results, written with numpy ranges instead of python-2 list ranges -----------
+def gen_batch_index(N_all, batch_size):
+    """utils/utils.py:45-74: index lists of consecutive batches, the last one possibly shorter."""
+    return [list(range(s, int(min(s + batch_size, N_all)))) for s in range(0, int(N_all), int(batch_size))]
+
+
+def gen_batch_npBool(N_all, batch_size):
+    """utils/utils.py:113-146 -> (N_batches, N_all) bool selectors."""
+    starts = np.arange(0, int(N_all), int(batch_size))
+    idx = np.arange(int(N_all))[None, :]
+    return (idx >= starts[:, None]) & (idx < starts[:, None] + int(batch_size))
+
+
+def yield_batch_npBool(N_all, batch_size):
+    """utils/utils.py:149-178: the rows of gen_batch_npBool one at a time."""
+    for row in gen_batch_npBool(N_all, batch_size):
+        yield row
+
+
+def gen_non0Batch_npBool(boolIndicators, batch_size):
+    """utils/utils.py:77-110: selectors over ALL elements that pick, batch by batch, the elements whose indicator is True."""
+    boolIndicators = np.asarray(boolIndicators).astype(bool)
+    order = np.cumsum(boolIndicators)                                   # 1-based rank of every True element
+    n_true = int(boolIndicators.sum())
+    sel = [(order >= s + 1) & (order <= min(s + int(batch_size), n_true)) & boolIndicators for s in range(0, n_true, int(batch_size))]
+    return np.array(sel) if sel else np.zeros((0, boolIndicators.size), dtype=bool)
+
+
+def yield_batch_ij_npBool(ij_lists, batch_size):
+    """utils/utils.py:181-230: batches of (i, j) index pairs enumerating ij_lists[0] x ij_lists[1] in row-major order."""
+    a, b = np.asarray(list(ij_lists[0])), np.asarray(list(ij_lists[1]))
+    i = np.repeat(a, b.size).astype(np.uint32)
+    j = np.tile(b, a.size).astype(np.uint32)
+    for s in range(0, i.size, int(batch_size)):
+        yield i[s:s + int(batch_size)], j[s:s + int(batch_size)]

@@ -182,3 +182,20 @@ def test_whole_scene_reconstruction_runs_end_to_end(tmp_path, cams):
     last = adapthresh.adapthresh(save_result_fld=str(tmp_path), N_refine_iter=2, D_cube=26, init_probThresh=0.5, min_probThresh=0.5,
                                  max_probThresh=0.9, rayPool_thresh=0, beta=6, gamma=0.8, npz_file=out["npz_path"], RGB_visual_ply=False)
     assert os.path.exists(last) and last.endswith("iter1.ply")
+
+
+def test_perspectiveProj_cubesCorner_matches_oracle(cams):
+    """utils/camera.py:186-250: (N_Ms, N_pts, 8) projections of the cube corners == the oracle's perspectiveProj of the same corners."""
+    from oracle import camera_oracle
+    from surfacenet_b200 import camera
+    xyz = np.array([[10.0, -30.0, 620.0], [30.0, 0.0, 650.0], [-20.5, 12.25, 600.0]], np.float32)
+    D_mm = np.float32(0.4) * 64
+    h, w = camera.perspectiveProj_cubesCorner(cams[[3, 8]], xyz, D_mm, return_int_hw=False)
+    assert h.shape == w.shape == (2, 3, 8)
+    corners = (xyz[:, None, :] + np.indices((2, 2, 2)).reshape((3, -1)).T[None] * D_mm).reshape(-1, 3)
+    ho, wo = camera_oracle.perspectiveProj(cams[[3, 8]], corners, return_int_hw=False)
+    assert np.array_equal(h.reshape(2, -1), ho) and np.array_equal(w.reshape(2, -1), wo)
+    hi, wi = camera.perspectiveProj_cubesCorner(cams[3], xyz[0], D_mm, return_int_hw=True)
+    assert hi.shape == (1, 1, 8) and hi.dtype == np.int64
+    with pytest.raises(ValueError):
+        camera.perspectiveProj_cubesCorner(np.zeros((4, 4)), xyz, D_mm)

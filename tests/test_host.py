@@ -267,3 +267,66 @@ def test_bench_simnet_reference_arm_json():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "patches/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+def test_batching_helpers_reference_doctest_known_answers():
+    """utils/utils.py:45-230: the reference's doctest answers for the host-side batching helpers."""
+    from surfacenet_b200 import utils as U
+    assert U.gen_batch_index(6, 3) == [[0, 1, 2], [3, 4, 5]] and U.gen_batch_index(7, 3) == [[0, 1, 2], [3, 4, 5], [6]]
+    assert U.gen_batch_index(8, 3) == [[0, 1, 2], [3, 4, 5], [6, 7]]
+    assert U.gen_batch_npBool(6, 3).tolist() == [[True] * 3 + [False] * 3, [False] * 3 + [True] * 3]
+    assert U.gen_batch_npBool(6, 100).tolist() == [[True] * 6]
+    sel = U.gen_batch_npBool(7, 3)
+    assert sel.tolist() == [[True, True, True, False, False, False, False], [False, False, False, True, True, True, False],
+                            [False, False, False, False, False, False, True]]
+    assert np.arange(14).reshape((7, 2))[sel[2]].tolist() == [[12, 13]]
+    ind = np.array([0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 1], dtype=bool)
+    s = U.gen_non0Batch_npBool(ind, 3)
+    assert s.shape == (3, 11)
+    assert s[0].tolist() == [bool(x) for x in [0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0]] and s[1].tolist() == [bool(x) for x in [0, 0, 0, 0, 0, 0, 1, 0, 1, 1, 0]]
+    assert s[2].tolist() == [bool(x) for x in [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1]]
+    feat = np.arange(3 * 6 * 8).reshape((3, 6, 8))
+    b1 = [feat[i, j] for i, j in U.yield_batch_ij_npBool((range(3), range(6)), 5)]
+    b2 = [feat.reshape((18, 8))[b] for b in U.gen_batch_npBool(18, 5)]
+    assert len(b1) == len(b2) == 4 and all(np.array_equal(x, y) for x, y in zip(b1, b2))
+    assert [b.sum() for b in U.yield_batch_npBool(7, 3)] == [3, 3, 1]
+    assert U.k_combination_np([2, 5, 8]).tolist() == [[2, 5], [2, 8], [5, 8]] and U.k_combination_np([2, 5, 8]).dtype == np.int64
+    assert np.allclose(U.k_combination_np([2.2, 5.5, 8.8, 9.9], k=3), [[2.2, 5.5, 8.8], [2.2, 5.5, 9.9], [2.2, 8.8, 9.9], [5.5, 8.8, 9.9]])
+
+
+def test_scene_and_camera_host_reference_doctest_known_answers():
+    """utils/scene.py:24-40 (initializeCubes) and utils/camera.py:88-96 (__cameraP2T__) known answers."""
+    from surfacenet_b200 import camera, reconstruct
+    cubes, side = reconstruct.initialize_cubes(resol=1, cube_D=22, cube_Dcenter=10, cube_overlapping_ratio=0.5,
+                                               BB=np.array([[3, 88], [-11, 99], [-110, -11]]))
+    assert side == 22
+    # the doctest at scene.py:28-36 prints the first cube at BB_min; the CODE below it (scene.py:43-58, the version that produced the
+    # shipped log's 24,420 cubes) starts at BB_min - (cube_D - cube_Dcenter) * resol / 2 = BB_min - 6: the code is followed
+    assert cubes["xyz"][:3].tolist() == [[-3., -17., -116.], [-3., -17., -111.], [-3., -17., -106.]] and cubes["ijk"][:3].tolist() == [[0, 0, 0], [0, 0, 1], [0, 0, 2]]
+    n_z = int(np.ceil(((-11 + 6) - (-110 - 6)) / 5.0))
+    assert cubes["ijk"][n_z].tolist() == [0, 1, 0] and cubes["xyz"][n_z].tolist() == [-3., -12., -116.]
+    assert np.all(cubes["resol"] == 1.0)
+    P = np.array([[798.693916, -2438.153488, 1568.674338, -542599.034996], [-44.838945, 1433.912029, 2576.399630, -1176685.647358],
+                  [-0.840873, -0.344537, 0.417405, 382.793511]])
+    assert np.allclose(camera.__cameraP2T__(P), [555.64348632032, 191.10837560939, 360.02470478273])
+    assert np.allclose(camera.cameraPs2Ts(np.stack([P, P]))[1], camera.__cameraP2T__(P)) and isinstance(camera.cameraPs2Ts([P]), list)
+
+
+def test_new_dropins_have_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from surfacenet_b200 import adapthresh, camera, denoising, earlyRejection, similarityNet, viewPairSelection
+    ijk, mask = [np.array([[1, 0, 0]], np.uint8)], [np.ones(1, bool)]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        denoising.denoise_crossCubes(np.zeros((1, 3), np.int32), ijk, mask, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        adapthresh.adapthresh_lists([np.ones(1, np.float16)], ijk, [np.ones(1, np.uint8)], np.zeros((1, 3), np.int32), 1, 4, 0.5, 0.9, 0, 6)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        similarityNet.similarityNet_inference(similarityNet.synthetic_params(0), (64, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        earlyRejection.selectFromSimilarity(np.zeros((2, 3), np.float32), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        viewPairSelection.__argmaxN_viewPairs__(np.array([[0, 1]]), np.ones((1, 1)), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        camera.viewPairAngles_wrt_pts(np.zeros((2, 3)), np.ones((1, 3)))

@@ -52,6 +52,38 @@ class DeviceSparseCubes:
             raise ValueError("sparse cubes: bad sizes (C={}, N={}, G={})".format(self.C, self.N, self.G))
         self.ws = torch.empty(int(need), dtype=torch.uint8, device="cuda")
 
+    @classmethod
+    def from_flat(cls, cube_ijk_np, offsets, ijk, pred=None, votes=None, grid_extent=None):
+        """The same object from the flat arrays of the NPZ file / of HotPath.infer_batch_sparse (numpy arrays or cuda tensors):
+        cube_ijk_np (C,3) int, offsets (C+1,) = cube_1st_vxlIndx_np, ijk (N,3) uint8, pred (N,) float16, votes (N,) uint8.  No per-cube
+        python lists are built; grid_extent defaults to max(ijk) + 1."""
+        torch = _lib.require_cuda()
+        self = cls.__new__(cls)
+        self.torch = torch
+        dev = lambda a, dt: (a.to(device="cuda", dtype=dt) if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a).astype(dt_np[dt], copy=False)).cuda()).contiguous()
+        dt_np = {torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8, torch.float16: np.float16}
+        self.cube_ijk = dev(np.asarray(cube_ijk_np).astype(np.int64) if not torch.is_tensor(cube_ijk_np) else cube_ijk_np, torch.int32).reshape(-1, 3)
+        self.offsets = dev(offsets, torch.int64)
+        self.offsets_np = self.offsets.cpu().numpy()
+        self.C, self.N = int(self.cube_ijk.shape[0]), int(self.offsets_np[-1]) if self.offsets_np.size else 0
+        if self.offsets_np.size != self.C + 1 or (self.C and np.any(np.diff(self.offsets_np) < 0)):
+            raise ValueError("offsets must be a non-decreasing array of {} entries".format(self.C + 1))
+        self.sizes = np.diff(self.offsets_np)
+        self.ijk = dev(ijk, torch.uint8).reshape(-1, 3)
+        if int(self.ijk.shape[0]) != self.N:
+            raise Warning('make sure # of voxels in each cube are consistent.')
+        self.G = int(grid_extent) if grid_extent is not None else (int(self.ijk.max().item()) + 1 if self.N else 1)
+        self.pred = None if pred is None else dev(pred, torch.float16).reshape(-1)
+        self.votes = None if votes is None else dev(votes, torch.uint8).reshape(-1)
+        for t in (self.pred, self.votes):
+            if t is not None and int(t.shape[0]) != self.N:
+                raise Warning('make sure # of voxels in each cube are consistent.')
+        need = _lib.lib.sn_sparse_post_workspace_bytes(self.C, self.N, self.G)
+        if need < 0:
+            raise ValueError("sparse cubes: bad sizes (C={}, N={}, G={})".format(self.C, self.N, self.G))
+        self.ws = torch.empty(int(need), dtype=torch.uint8, device="cuda")
+        return self
+
     # ---- list <-> flat -------------------------------------------------------------------------------------------
     def upload_mask(self, vxl_mask_list):
         m = _flat([np.asarray(x).astype(bool) for x in vxl_mask_list], np.uint8)

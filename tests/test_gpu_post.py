@@ -216,3 +216,21 @@ def test_post_errors_and_empty():
     keep = denoising.denoise_crossCubes(np.array([[0, 0, 0], [1, 0, 0]]), [np.zeros((0, 3), np.uint8), np.array([[1, 2, 3]], np.uint8)],
                                         [np.zeros(0, bool), np.zeros(1, bool)], 8)
     assert [k.tolist() for k in keep] == [[], [False]]
+
+
+def test_from_flat_equals_list_constructor():
+    """DeviceSparseCubes.from_flat (the NPZ / infer_batch_sparse arrays, no python lists) == the list constructor."""
+    import torch
+    from surfacenet_b200.sparse_device import DeviceSparseCubes
+    sc = util.sparse_scene((2, 2, 2), 16, seed=13)
+    a = DeviceSparseCubes(sc["cube_ijk"], sc["ijk_list"], sc["pred_list"], sc["votes_list"])
+    off = np.concatenate([[0], np.cumsum([x.shape[0] for x in sc["ijk_list"]])]).astype(np.uint32)     # cube_1st_vxlIndx_np dtype
+    b = DeviceSparseCubes.from_flat(sc["cube_ijk"], off, np.vstack(sc["ijk_list"]), np.concatenate(sc["pred_list"]), np.concatenate(sc["votes_list"]))
+    c = DeviceSparseCubes.from_flat(a.cube_ijk, a.offsets, a.ijk, a.pred, a.votes, grid_extent=16)       # cuda tensors in
+    for x in (b, c):
+        assert (x.C, x.N) == (a.C, a.N) and x.G in (a.G, 16)
+        m = x.filter_voxels(None, prob_thresh=0.6, rayPool_thresh=4)
+        assert torch.equal(m, a.filter_voxels(None, prob_thresh=0.6, rayPool_thresh=4))
+        assert torch.equal(x.denoise(m, 16)["keep"], a.denoise(m, 16)["keep"])
+    with pytest.raises(ValueError):
+        DeviceSparseCubes.from_flat(sc["cube_ijk"], off[:-1], np.vstack(sc["ijk_list"]))

@@ -330,3 +330,26 @@ def test_new_dropins_have_no_cpu_fallback():
         viewPairSelection.__argmaxN_viewPairs__(np.array([[0, 1]]), np.ones((1, 1)), 1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         camera.viewPairAngles_wrt_pts(np.zeros((2, 3)), np.ones((1, 3)))
+
+
+def test_similarityNet_model_file_roundtrip(tmp_path):
+    """nets/similarityNet.py:241-244: the model file is a pickled list of the 30 parameter arrays (python-2 protocol)."""
+    import pickle
+    from surfacenet_b200 import similarityNet
+    params = similarityNet.synthetic_params(1)
+    assert len(params) == 30 and [p.shape for p in params] == [tuple(s) for s in similarityNet.PARAM_SHAPES]
+    f = tmp_path / "epoch33.model"
+    with open(f, "wb") as fh:
+        pickle.dump([np.asarray(p, np.float64) for p in params[:2]] + params[2:], fh, protocol=2)
+    back = similarityNet.load_model_file(str(f))
+    assert all(b.dtype == np.float32 and np.array_equal(a, b) for a, b in zip(params, back))
+
+
+def test_bench_post_reference_arm_json():
+    """bench.py --workload post --impl reference: the numpy/scipy post-processing restatement, one JSON line."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--workload", "post", "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "voxels/s" and line["value"] > 0 and line["cpu_baseline"]["cores"] == 1

@@ -33,6 +33,28 @@ def initialize_cubes(resol, cube_D, cube_Dcenter, cube_overlapping_ratio, BB):
     return cubes, side
 
 
+def quantize_pts_to_cubes(pts_xyz, resol, cube_D, cube_Dcenter, cube_overlapping_ratio, BB=None):
+    """Overlapping cubes covering a point cloud, same layout as utils/scene.py:63-107 (quantizePts2Cubes; main_reconstruct.py:57-60 when
+    an initial point cloud is given): every point selects the two neighbouring grid cells per axis (floor and floor + 1 of its
+    stride coordinate), the distinct cells are the cubes.  -> (cubes_param (N,) PARAM_DTYPE, cube side in mm)"""
+    pts_xyz = np.asarray(pts_xyz)
+    side, centre = resol * cube_D, resol * cube_Dcenter
+    stride = centre * cube_overlapping_ratio
+    if BB is not None:
+        BB = np.asarray(BB)
+        margin = side / 2
+        inBB = np.array([np.logical_and(pts_xyz[:, a] >= (BB[a, 0] - margin), pts_xyz[:, a] <= (BB[a, 1] + margin)) for a in range(3)]).all(axis=0)
+        pts_xyz = pts_xyz[inBB]
+    shift = pts_xyz.min(axis=0)[None, ...]
+    lo = (pts_xyz - shift) // stride
+    cells = np.unique(np.vstack([lo, lo + 1]), axis=0)                  # rows sorted lexicographically, like the structured np.unique
+    cubes = np.empty(cells.shape[0], dtype=PARAM_DTYPE)
+    cubes["ijk"] = cells
+    cubes["xyz"] = (cubes["ijk"] * stride + shift) - side / 2
+    cubes["resol"] = resol
+    return cubes, side
+
+
 def reconstruct_cubes(hot, cubes_param, viewPairs, w, cube_D, cube_Dcenter=None, batch_size=16, rayPool_thresh=0,
                       rank=0, world_size=1, progress=None):
     """main_reconstruct.py:119-166.  hot: pipeline.HotPath; cubes_param: structured array ('xyz','ijk','resol') of the valid

@@ -353,3 +353,14 @@ def test_bench_post_reference_arm_json():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "voxels/s" and line["value"] > 0 and line["cpu_baseline"]["cores"] == 1
+
+
+def test_cube_grid_builders_match_reference_outputs():
+    """utils/scene.py:7-107 executed by tests/golden/make_golden_scene.py: the scan9 grid (24,420 cubes, q.log) and quantizePts2Cubes."""
+    from surfacenet_b200 import reconstruct
+    g = np.load(os.path.join(REPO, "tests", "golden", "scene_golden.npz"))
+    cubes, side = reconstruct.initialize_cubes(np.float32(0.4), 64, 52, 0.5, np.array([[-73., 129.], [-197., 183.], [472., 810.]]))
+    assert len(cubes) == int(g["init_n"][0]) == 24420
+    assert np.array_equal(cubes["xyz"][::997], g["init_xyz_sample"]) and np.array_equal(cubes["ijk"][::997], g["init_ijk_sample"])
+    q, D_mm = reconstruct.quantize_pts_to_cubes(g["q_pts"], np.float32(0.4), 32, 26, 0.5, BB=np.array([[0., 40.], [-5., 20.], [598., 612.]]))
+    assert D_mm == g["q_D_mm"][0] and np.array_equal(q["ijk"], g["q_ijk"]) and np.array_equal(q["xyz"], g["q_xyz"]) and np.array_equal(q["resol"], g["q_resol"])

@@ -84,3 +84,33 @@ def perspectiveProj_cubesCorner(projection_M, cube_xyz_min, cube_D_mm, return_in
     cubeCorner = cube_xyz_min[:, None, :] + cubeCorner_shift
     img_h, img_w = perspectiveProj(projection_M=projection_M, xyz_3D=cubeCorner.reshape((N_pts * 8, 3)), return_int_hw=return_int_hw)
     return img_h.reshape((-1, N_pts, 8)), img_w.reshape((-1, N_pts, 8))
+
+
+def __readCameraPO_as_np_DTU__(cameraPO_file):
+    """utils/camera.py:7-24: one (3,4) float64 projection matrix per text file."""
+    return np.loadtxt(cameraPO_file, dtype=np.float64, delimiter=' ')
+
+
+def __readCameraPOs_as_np_Middlebury__(cameraPO_file, viewList):
+    """utils/camera.py:26-53: `name K(9) R(9) t(3)` per line after a count line; P = K [R | t]; line n <-> view n (1-based)."""
+    with open(cameraPO_file) as f:
+        lines = f.readlines()
+    cameraPOs = np.empty((len(lines), 3, 4)).astype(np.float64)
+    for _n, _l in enumerate(lines):
+        if _n == 0:
+            continue
+        _params = np.array(_l.strip().split(' ')[1:], dtype=np.float64)
+        cameraPOs[_n] = np.dot(_params[:9].reshape((3, 3)), np.c_[_params[9:18].reshape((3, 3)), _params[18:].reshape((3, 1))])
+    return cameraPOs[list(viewList)]
+
+
+def readCameraPOs_as_np(datasetFolder, datasetName, poseNamePattern, model, viewList):
+    """utils/camera.py:55-82 -> (N_views,3,4) float64; '#' -> zero-padded view index, '@' -> plain view index."""
+    import os
+    if 'Middlebury' in datasetName:
+        return __readCameraPOs_as_np_Middlebury__(os.path.join(datasetFolder, poseNamePattern), viewList)
+    cameraPOs = np.empty((len(viewList), 3, 4), dtype=np.float64)
+    for _i, _view in enumerate(viewList):
+        cameraPOs[_i] = __readCameraPO_as_np_DTU__(os.path.join(
+            datasetFolder, poseNamePattern.replace('#', '{:03}'.format(_view)).replace('@', '{}'.format(_view))))
+    return cameraPOs

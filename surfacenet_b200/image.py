@@ -48,3 +48,17 @@ def cropImgPatches(img, range_h, range_w, patchSize=64, pyramidRate=1.2, interp_
         center_h, center_w = cubeCenter_hw
     out = crop_preprocessed_patches_device(torch.from_numpy(img).cuda(), center_h, center_w, patchSize, np.zeros(3, np.float32))
     return np.ascontiguousarray(out.cpu().numpy()[:, ::-1].transpose(0, 2, 3, 1)).astype(np.uint8)      # BGR (c,h,w) -> RGB (h,w,c)
+
+
+def readImages(datasetFolder, imgNamePattern, viewList, return_list=True):
+    """utils/image.py:50-89: the images of the listed views as (H,W,3) uint8 arrays ('#' -> zero-padded view index, '@' -> plain);
+    decoded with PIL (the reference's scipy.misc.imread was a PIL wrapper)."""
+    import os
+    from PIL import Image
+    imgs_list = []
+    for viewIndx in viewList:
+        imgPath = os.path.join(datasetFolder, imgNamePattern.replace('#', '{:03}'.format(viewIndx)).replace('@', '{}'.format(viewIndx)))
+        with Image.open(imgPath) as im:
+            imgs_list.append(np.asarray(im.convert("RGB") if im.mode not in ("RGB", "L") else im))
+        print('loaded img ' + imgPath)
+    return imgs_list if return_list else np.stack(imgs_list)

@@ -364,3 +364,23 @@ def test_cube_grid_builders_match_reference_outputs():
     assert np.array_equal(cubes["xyz"][::997], g["init_xyz_sample"]) and np.array_equal(cubes["ijk"][::997], g["init_ijk_sample"])
     q, D_mm = reconstruct.quantize_pts_to_cubes(g["q_pts"], np.float32(0.4), 32, 26, 0.5, BB=np.array([[0., 40.], [-5., 20.], [598., 612.]]))
     assert D_mm == g["q_D_mm"][0] and np.array_equal(q["ijk"], g["q_ijk"]) and np.array_equal(q["xyz"], g["q_xyz"]) and np.array_equal(q["resol"], g["q_resol"])
+
+
+def test_camera_and_image_file_readers(tmp_path):
+    """utils/camera.py:7-82, utils/image.py:50-89: the readers against matrices the reference readers produced from the bundled DTU / Middlebury
+    calibration files (the file texts are stored in the fixture, generated in the build container)."""
+    from PIL import Image
+    from surfacenet_b200 import camera, image
+    g = np.load(os.path.join(REPO, "tests", "golden", "camera_files_golden.npz"))
+    os.makedirs(tmp_path / "cal18")
+    for v, txt in zip((1, 10, 49), g["dtu_text"]):
+        (tmp_path / "cal18" / ("pos_%03d.txt" % v)).write_text(str(txt))
+    P = camera.readCameraPOs_as_np(str(tmp_path), "DTU", "cal18/pos_#.txt", 9, [1, 10, 49])
+    assert P.dtype == np.float64 and np.array_equal(P, g["P_dtu"])
+    (tmp_path / "dinoSR_par.txt").write_text(str(g["mid_par_text"]))
+    Pm = camera.readCameraPOs_as_np(str(tmp_path), "Middlebury", "dinoSR_par.txt", "dinoSparseRing", list(range(7, 13)))
+    assert np.array_equal(Pm, g["P_mid"])
+    img = util.synth_image(1, 30, 40)
+    Image.fromarray(img).save(str(tmp_path / "rect_007_3.png"))
+    back = image.readImages(str(tmp_path), "rect_#_3.png", [7, 7], return_list=False)
+    assert back.shape == (2, 30, 40, 3) and back.dtype == np.uint8 and np.array_equal(back[0], img)

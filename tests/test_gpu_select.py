@@ -199,3 +199,4 @@ def test_perspectiveProj_cubesCorner_matches_oracle(cams):
     assert hi.shape == (1, 1, 8) and hi.dtype == np.int64
     with pytest.raises(ValueError):
         camera.perspectiveProj_cubesCorner(np.zeros((4, 4)), xyz, D_mm)
+

@@ -384,3 +384,25 @@ def test_camera_and_image_file_readers(tmp_path):
     Image.fromarray(img).save(str(tmp_path / "rect_007_3.png"))
     back = image.readImages(str(tmp_path), "rect_#_3.png", [7, 7], return_list=False)
     assert back.shape == (2, 30, 40, 3) and back.dtype == np.uint8 and np.array_equal(back[0], img)
+
+
+def test_main_reconstruct_dropin_reads_inputs_then_needs_gpu(tmp_path):
+    """surfacenet_b200.main_reconstruct.reconstruction: the reference's argument list; without a GPU it gets through the file readers and
+    then refuses to run (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from PIL import Image
+    from surfacenet_b200 import main_reconstruct, similarityNet, weights
+    cams = util.dtu_cameras()
+    os.makedirs(tmp_path / "cal")
+    for v in (1, 2):
+        np.savetxt(str(tmp_path / "cal" / ("pos_%03d.txt" % v)), cams[v - 1], delimiter=' ')
+        Image.fromarray(util.synth_image(v, 120, 160)).save(str(tmp_path / ("rect_%03d.png" % v)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#.png", "cal/pos_#.txt", None, str(tmp_path / "out"), 1, np.float32(0.4),
+                                        np.array([[0., 10.], [0., 10.], [600., 610.]]), [1, 2], surfacenet_model=weights.synthetic_params(0),
+                                        similnet_model=similarityNet.synthetic_params(0), cube_D=32)
+    with pytest.raises(NotImplementedError):
+        main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#.png", "cal/pos_#.txt", "pts.ply", str(tmp_path / "out"), 1, np.float32(0.4),
+                                        np.zeros((3, 2)), [1, 2])

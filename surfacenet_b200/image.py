@@ -59,6 +59,6 @@ def readImages(datasetFolder, imgNamePattern, viewList, return_list=True):
     for viewIndx in viewList:
         imgPath = os.path.join(datasetFolder, imgNamePattern.replace('#', '{:03}'.format(viewIndx)).replace('@', '{}'.format(viewIndx)))
         with Image.open(imgPath) as im:
-            imgs_list.append(np.asarray(im.convert("RGB") if im.mode not in ("RGB", "L") else im))
+            imgs_list.append(np.array(im.convert("RGB") if im.mode not in ("RGB", "L") else im))       # a writable copy
         print('loaded img ' + imgPath)
     return imgs_list if return_list else np.stack(imgs_list)

@@ -200,3 +200,22 @@ def test_perspectiveProj_cubesCorner_matches_oracle(cams):
     with pytest.raises(ValueError):
         camera.perspectiveProj_cubesCorner(np.zeros((4, 4)), xyz, D_mm)
 
+
+
+def test_main_reconstruct_dropin_from_files(tmp_path, cams):
+    """surfacenet_b200.main_reconstruct.reconstruction with the reference's argument list: images / cameras read from files, NPZ path back."""
+    from PIL import Image
+    from surfacenet_b200 import main_reconstruct, similarityNet, sparseCubes, weights
+    views = [3, 8, 15, 22]
+    os.makedirs(tmp_path / "cal")
+    for v in views:
+        np.savetxt(str(tmp_path / "cal" / ("pos_%03d.txt" % v)), cams[v], delimiter=' ')
+        Image.fromarray(util.synth_image(200 + v, 1200, 1600)).save(str(tmp_path / ("rect_%03d_3.png" % v)))
+    sp = similarityNet.synthetic_params(0)
+    sp[28] = np.array([[-0.02]], np.float32); sp[29] = np.array([-0.4], np.float32)
+    npz = main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#_3.png", "cal/pos_#.txt", None, str(tmp_path / "out"), 2, np.float32(0.4),
+                                          np.array([[-10.0, 15.0], [-20.0, 5.0], [620.0, 645.0]]), views, surfacenet_model=weights.synthetic_params(0),
+                                          similnet_model=sp, cube_D=32, tau=0.5, gamma=0.0)
+    assert npz.endswith("model9-4views.npz") and os.path.exists(npz)
+    back = sparseCubes.load_sparseCubes(npz)
+    assert len(back[0]) > 0 and back[6].shape[1:] == (2, 2) and os.path.exists(str(tmp_path / "out" / "fixThresh_tau0.5_gamma0.0.ply"))

@@ -41,7 +41,7 @@ class Net:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
         return self._ws
 
-    def forward(self, X, w=None, N_vp=1, mode="fp32", want_unfused=True):
+    def forward(self, X, w=None, N_vp=1, mode="exact", want_unfused=True):
         """X torch.cuda (B*N_vp,6,D,D,D) f32 (mean subtracted); w torch.cuda (B,N_vp) f32 or None."""
         torch = _lib.require_cuda()
         if X.dim() != 5 or X.shape[1] != 6 or X.shape[2] != X.shape[3] or X.shape[3] != X.shape[4]:
@@ -55,7 +55,7 @@ class Net:
             if tuple(w.shape) != (B, N_vp):
                 raise ValueError("w must have shape ({}, {}), got {}".format(B, N_vp, tuple(w.shape)))
         X = X.contiguous()
-        m = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+        m = _lib.resolve_mode(mode)
         fused = torch.empty((B, 1, D, D, D), dtype=torch.float32, device="cuda")
         unf = torch.empty((B, N_vp, D, D, D), dtype=torch.float32, device="cuda") if (want_unfused and N_vp > 1) else None
         need = _lib.lib.sn_net_workspace_bytes(self.handle, B * N_vp, D, m)
@@ -85,7 +85,7 @@ def _to_dev(torch, a):
     return a.to(device="cuda", dtype=torch.float32), False
 
 
-def make_inference_fns(net, N_viewPairs4inference, mode="fp32"):
+def make_inference_fns(net, N_viewPairs4inference, mode="exact"):
     """The two callables nets/SurfaceNet.py:382 compiles, bound to ``net``."""
     N_vp = int(N_viewPairs4inference)
 
@@ -110,11 +110,13 @@ def make_inference_fns(net, N_viewPairs4inference, mode="fp32"):
     return viewPair_relativeImpt_fn, nViewPair_SurfaceNet_fn
 
 
-def SurfaceNet_inference(N_viewPairs4inference, model_file, layerNameList_2_load=None, mode="fp32"):
+def SurfaceNet_inference(N_viewPairs4inference, model_file, layerNameList_2_load=None, mode="exact"):
     """nets/SurfaceNet.py:385-402.  ``model_file``: path of the reference's pickled parameter list
     (or .npz), or an in-memory list of the 105 arrays.  ``layerNameList_2_load`` is accepted for call
     compatibility: the reference always loads ["output_SurfaceNet_reshape","output_softmaxWeights"]
-    (params.py:105), i.e. the whole 105-array list."""
+    (params.py:105), i.e. the whole 105-array list.
+    ``mode``: "exact" (default; tcgen05 tensor cores, fp16 hi/lo split operands, <= 1e-4 on the probability),
+    "fp32" (CUDA-core cross-check, ~26x slower), "fast" (single-pass fp16 operands: MISSES the 1e-4 bound, warns)."""
     if layerNameList_2_load is not None and list(layerNameList_2_load) != ["output_SurfaceNet_reshape", "output_softmaxWeights"]:
         raise ValueError("only the full parameter list of params.py:105 can be loaded, got {}".format(layerNameList_2_load))
     params = weights.load_model_file(model_file) if isinstance(model_file, str) else model_file

@@ -83,7 +83,7 @@ topn_rows_kernel(const double* __restrict__ w, int n, int n_pad, int N, int32_t*
     int* idx = (int*)(key + n_pad);
     const double* row = w + (int64_t)blockIdx.x * n;
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-        key[i] = i < n ? row[i] : INFINITY;               // padding sorts last (index breaks ties with real +inf entries)
+        key[i] = i < n ? row[i] : INFINITY;               // padding (idx >= n) sorts after every real entry, NaN included
         idx[i] = i;
     }
     __syncthreads();
@@ -95,7 +95,9 @@ topn_rows_kernel(const double* __restrict__ w, int n, int n_pad, int N, int32_t*
                     const bool up = (i & k) == 0;
                     const double a = key[i], b = key[l];
                     const int ia = idx[i], ib = idx[l];
-                    const bool a_gt_b = (a > b) || (a == b && ia > ib) || (a != a && b == b);    // NaN sorts last like numpy
+                    // order: real values ascending (ties by index) < NaN entries (by index, numpy sorts NaN last) < padding
+                    const bool pa = ia >= n, pb = ib >= n, na = a != a, nb = b != b;
+                    const bool a_gt_b = (pa != pb) ? pa : ((na != nb) ? na : ((na || a == b) ? ia > ib : a > b));
                     if (a_gt_b == up) { key[i] = b; key[l] = a; idx[i] = ib; idx[l] = ia; }
                 }
             }

@@ -16,11 +16,11 @@ MIN_PROB = 0.46          # params.py:66  __min_prob
 
 
 class HotPath:
-    def __init__(self, net, scene, mode="fp32", min_prob=MIN_PROB):
+    def __init__(self, net, scene, mode="exact", min_prob=MIN_PROB):
         """net: SurfaceNet.Net; scene: DeviceScene (images + cameras resident on the device)."""
         self.torch = _lib.require_cuda()
         self.net, self.scene = net, scene
-        self.mode = _lib.MODES[mode] if isinstance(mode, str) else int(mode)
+        self.mode = _lib.resolve_mode(mode)
         self.min_prob = float(min_prob)
         self._ws = None
         self._pinned = {}

@@ -13,6 +13,7 @@ def __argmaxN_viewPairs__(viewPairs, w_viewPairs, N_argmax):
     if w_viewPairs.ndim != 2 or viewPairs.shape != (w_viewPairs.shape[1], 2):
         raise ValueError("need viewPairs (N_viewPairs,2) and w_viewPairs (N_validCubes,N_viewPairs), got {} {}".format(viewPairs.shape, w_viewPairs.shape))
     rows, n = w_viewPairs.shape
+    N_argmax = min(int(N_argmax), n)              # argsort()[:, -N:] returns all n columns when N > n (viewPairSelection.py:36)
     w = torch.from_numpy(np.ascontiguousarray(w_viewPairs, dtype=np.float64)).cuda()
     idx = torch.zeros((rows, N_argmax), dtype=torch.int32, device="cuda")
     _lib.check(_lib.lib.sn_topn_rows(_lib.ptr(w), rows, n, int(N_argmax), _lib.ptr(idx), _lib.stream_ptr()))

@@ -56,8 +56,15 @@ def test_argmaxN_viewPairs_reference_doctest_and_golden(g, case):
     a, b = vps.__argmaxN_viewPairs__(vp49, big, 5)
     idx = np.argsort(big, axis=1, kind="stable")[:, -5:]
     assert np.array_equal(a, vp49[idx]) and np.array_equal(b, np.take_along_axis(big, idx, axis=1))
-    with pytest.raises(ValueError):
-        vps.__argmaxN_viewPairs__(vp, w, 4)
+    a, b = vps.__argmaxN_viewPairs__(vp, w, 4)                           # N > n: argsort()[:, -4:] returns all 3 columns
+    assert a.shape == (2, 3, 2) and b.tolist() == [[1, 2, 3], [-1, 0, 70]]
+    # NaN rows with n not a power of two: numpy sorts NaN last, so NaN entries are among the "largest" (index order)
+    wn = np.array([[0.5, np.nan, 0.1, 0.9, np.nan, 0.3, 0.2], [np.nan] * 7, [1, 2, 3, 4, 5, 6, 7.]])
+    vp7 = np.stack([np.arange(7), np.arange(7) + 1], axis=1)
+    a, b = vps.__argmaxN_viewPairs__(vp7, wn, 3)
+    idx = np.argsort(wn, axis=1, kind="stable")[:, -3:]
+    assert np.array_equal(a, vp7[idx]) and np.array_equal(np.isnan(b), np.isnan(np.take_along_axis(wn, idx, axis=1)))
+    assert idx.max() < 7 and a.max() <= 7
 
 
 def test_crop_and_preprocess_bit_exact(g, case):

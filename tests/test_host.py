@@ -406,3 +406,69 @@ def test_main_reconstruct_dropin_reads_inputs_then_needs_gpu(tmp_path):
     with pytest.raises(NotImplementedError):
         main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#.png", "cal/pos_#.txt", "pts.ply", str(tmp_path / "out"), 1, np.float32(0.4),
                                         np.zeros((3, 2)), [1, 2])
+
+
+_WORKER_RECON = """
+import os, sys
+sys.path.insert(0, {repo!r})
+import numpy as np, torch.distributed as dist
+from surfacenet_b200 import reconstruct
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+class FakeHot:                       # stands in for pipeline.HotPath.infer_batch_sparse (no GPU): deterministic per cube
+    def infer_batch_sparse(self, pairs, xyz, resol, w, D, Dc, thresh):
+        counts = np.array([int(abs(x[0])) % 4 for x in xyz], np.int32)          # some cubes are empty
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        T = int(off[-1])
+        seed = np.repeat(np.asarray(xyz)[:, 0], counts).astype(np.float32)
+        return dict(counts=counts, offsets=off, ijk=(np.arange(T * 3).reshape(T, 3) % 7).astype(np.uint8), pred=(seed / 100).astype(np.float16),
+                    rgb=np.full((T, 3), 9, np.uint8), votes=(seed.astype(np.int64) % 5).astype(np.uint8))
+
+n = {n}
+cubes = np.zeros(n, dtype=reconstruct.PARAM_DTYPE)
+cubes["xyz"] = np.arange(n * 3, dtype=np.float32).reshape(n, 3); cubes["ijk"] = np.arange(n * 3).reshape(n, 3); cubes["resol"] = 0.4
+pairs = np.arange(n * 4).reshape(n, 2, 2); w = np.ones((n, 2), np.float32)
+whole = reconstruct.reconstruct_cubes(FakeHot(), cubes, pairs, w, 32, 26, batch_size=2)
+got = reconstruct.reconstruct_cubes(FakeHot(), cubes, pairs, w, 32, 26, batch_size=2, rank=rank, world_size=world, gather=True)
+part = reconstruct.reconstruct_cubes(FakeHot(), cubes, pairs, w, 32, 26, batch_size=2, rank=rank, world_size=world)
+assert len(part[0]) < len(whole[0])                                        # a rank alone holds only its share
+for a, b in zip(whole[:4], got[:4]):
+    assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b)), "rank %d: gathered lists differ" % rank
+for a, b in zip(whole[4:], got[4:]):
+    assert np.array_equal(a, b), "rank %d: gathered cube tables differ" % rank
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_reconstruct_cubes_gather_gloo_world2(tmp_path):
+    """world_size 2: every rank ends up with the WHOLE scene in single-rank batch order before the cross-cube stages
+    (denoise_crossCubes / NPZ need every neighbour cube; main_reconstruct.py:168-183)."""
+    port = 29850 + os.getpid() % 100
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER_RECON.format(repo=REPO, port=port, n=9))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "OK %d" % r in o, o[-2000:]
+
+
+def test_initialize_cubes_float32_resol_uses_float64_arithmetic():
+    """params.py passes resol = np.float32(0.4); under the reference's numpy 1.x, float32_scalar * int is float64 arithmetic."""
+    from surfacenet_b200 import reconstruct
+    BB = [[-40, 40], [80, 160], [630, 680]]
+    cubes32, side32 = reconstruct.initialize_cubes(np.float32(0.4), 64, 52, 0.5, BB)
+    r = float(np.float32(0.4))
+    stride, margin = r * 52 * 0.5, (r * 64 - r * 52) / 2
+    n_axis = [int(np.ceil(((b[1] + margin) - (b[0] - margin)) / stride)) for b in BB]
+    ijk = np.indices(tuple(n_axis)).reshape(3, -1).T
+    want = (ijk * stride + (np.array(BB, np.float64)[:, 0][None] - margin)).astype(np.float32)
+    assert cubes32.shape[0] == ijk.shape[0] and np.array_equal(cubes32["xyz"], want) and side32 == r * 64
+    pts = np.random.default_rng(0).uniform(-30, 30, (50, 3))
+    q32, _ = reconstruct.quantize_pts_to_cubes(pts, np.float32(0.4), 64, 52, 0.5)
+    q64, _ = reconstruct.quantize_pts_to_cubes(pts, r, 64, 52, 0.5)
+    assert np.array_equal(q32["xyz"], q64["xyz"]) and np.array_equal(q32["ijk"], q64["ijk"])

@@ -22,8 +22,8 @@
 // (converged warp, one lane elected by elect.sync), 3 = TMEM allocator, 4..7 = epilogue (TMEM -> registers ->
 // folded BatchNorm + ReLU/sigmoid -> hi/lo split -> blk store, or the fused merge_conv3 1x1x1 + sigmoid -> fp32
 // probability).  The tile configuration (AD, NB, taps per slot, CTA scheduling) is measured once per unit.
-#include "net.cuh"
-#include <cuda.h>
+#include "tc_ptx.cuh"
+#include "tc_state.cuh"
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
@@ -32,83 +32,9 @@
 namespace sn {
 
 // ------------------------------------------------------------------------------------------------
-// PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// long waits (epilogue warps waiting for the whole main loop): back off so the spinning warps do not steal issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, kind::f16 (fp16 operands, fp32 accumulate)
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 "version 1"):
-//   bits [0,14) start >> 4, [16,30) leading (K-direction core-matrix) byte offset >> 4,
-//   [32,46) stride (M/N-direction 8-row group) byte offset >> 4, [46,48) version = 1, [61,64) layout = 0
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-
-// ------------------------------------------------------------------------------------------------
 constexpr int TC_THREADS = 256;
 constexpr int TC_TW = 8, TC_TH = 16;          // one accumulator = 16 rows (h) x 8 voxels (w) of one d-plane
 constexpr int EPI_BLK = 0, EPI_FINAL = 1;
-constexpr int TC_MAX_NT = 4;
 
 struct ConvTcParams {
     int S, n_pc, dil, K, taps, n_cblk, cg_in, NB, nbuf, TPS;   // TPS = taps per weight-ring slot: 1, K (the kw taps of one (kd,kh)) or K*K
@@ -136,29 +62,6 @@ struct ConvTcParams {
     const float* w3; float scale3, shift3; int c3; float* prob_out;
 };
 
-__device__ __forceinline__ float tc_act(float y, int act) {
-    if (act == SN_ACT_RELU) return fmaxf(y, 0.f);
-    if (act == SN_ACT_SIGMOID) return 1.f / (1.f + expf(-y));
-    return y;
-}
-
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-
-// exactly one lane of the (converged) warp gets true; ptxas then knows the guarded tcgen05 / TMA
-// instruction is issued once and emits it directly instead of a per-lane election loop
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 rx;\n\t"
-        ".reg .pred px;\n\t"
-        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-        "selp.u32 %0, 1, 0, px;\n\t"
-        "}" : "=r"(pred) :: "memory");
-    return pred != 0;
-}
 
 // AD = d-planes (M = 128 accumulators) per CTA; P = 2: exact mode, every plane owns TWO accumulators -- the
 // main one receives only A_hi*W_hi, the correction one A_lo*W_hi + A_hi*W_lo (2^-11 smaller).  tcgen05
@@ -203,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
     uint64_t* a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + NB;
     uint64_t* acc_full = bars + 4 + 2 * NB, *acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    uint32_t* pair_tbl = tmem_slot + 4;                               // [32] tap-pair descriptors of the last channel block (pair_last)
+    uint32_t* pair_tbl = tmem_slot + 4 + ((warp == 3) ? 32 : 0);      // [2][32] tap-pair descriptors of the last channel block (pair_last): one private copy per MMA-issuing warp
     const int pad = p.dil * (p.K / 2);
     const int nbuf = p.nbuf;
     const uint32_t buf_cols = (uint32_t)(AD * P * Nmax);
@@ -628,29 +531,6 @@ static inline int ew_blocks(long long total) { return (int)std::min<long long>(c
 
 // ------------------------------------------------------------------------------------------------
 // host side: weight preparation, tensor maps, launches
-struct TileCfg { int AD, NB, persist, tps; };          // d-planes per CTA, weight-ring depth, CTA scheduling (see conv_tc_launch_cfg)
-struct TcVariant {                                 // [0] exact (P = 2), [1] fast (P = 1): own N tiling and weight image
-    int n_ntiles = 0, nt_size[TC_MAX_NT] = {0, 0, 0, 0}, nt_off[TC_MAX_NT] = {0, 0, 0, 0}, nt_nc[TC_MAX_NT] = {0, 0, 0, 0};
-    long long nt_woff[TC_MAX_NT] = {0, 0, 0, 0};
-    unsigned char* w = nullptr;
-};
-struct TcUnit {
-    int Cin_pad = 0, Cout_pad = 0, taps = 0, pair_last = 0, nv_last = 0;
-    float* side_w = nullptr;                       // for side units with one-N-tile producers: [Cin_pad][16] fp32 (transposed)
-    TcVariant v[2];
-    float* scale = nullptr;                        // Cout_pad entries, zero for padded channels
-    float* shift = nullptr;
-};
-
-struct TcState {
-    TcUnit units[kNumUnits];
-    float* w3 = nullptr; float scale3 = 0.f, shift3 = 0.f;
-    PFN_cuTensorMapEncodeTiled encode = nullptr;
-    cudaStream_t side_stream = nullptr;            // the side-output branch (side convs + up-samplers) runs beside the main chain
-    cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    std::map<int, std::pair<TileCfg, long long>> tuned;     // (unit, mode, S) -> best tile configuration, work it was measured at
-};
-
 static int pad16(int c) { return (int)align_up(c, 16); }
 
 int tc_prepare(Net& net) {
@@ -760,12 +640,13 @@ int tc_prepare(Net& net) {
         SN_CUDA(cudaMemcpy(st->w3, w3.data(), w3.size() * 4, cudaMemcpyHostToDevice));
         st->scale3 = m3.h_scale[0]; st->shift3 = m3.h_shift[0];
     }
-    return SN_OK;
+    return wg_prepare(net);
 }
 
 void tc_destroy(Net& net) {
     TcState* st = (TcState*)net.tc;
     if (!st) return;
+    wg_destroy(net);
     for (int u = 0; u < kNumUnits; ++u) {
         cudaFree(st->units[u].v[0].w); cudaFree(st->units[u].v[1].w); cudaFree(st->units[u].scale); cudaFree(st->units[u].shift);
         cudaFree(st->units[u].side_w);
@@ -798,7 +679,7 @@ static void tune_file_save(const TcState* st) {
     fclose(f);
 }
 
-static int get_encode(TcState* st) {
+int tc_get_encode(TcState* st) {
     if (st->encode) return SN_OK;
     tune_file_load(st);
     void* fn = nullptr;
@@ -813,7 +694,7 @@ static size_t tc_smem_bytes(const ConvUnit& cu, int Nmax, int P, TileCfg c) {
     const int pad = cu.dil * (cu.K / 2);
     const int PW = TC_TW + 2 * pad, HH = TC_TH + 2 * pad;
     const int tps = c.tps == 2 ? cu.K * cu.K : (c.tps == 1 ? cu.K : 1);
-    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P * tps + (8 + 2 * c.NB) * 8 + 16 + 128;
+    return 2 * (size_t)PW * HH * (c.AD + 2 * pad) * 32 * P + (size_t)c.NB * Nmax * 32 * P * tps + (8 + 2 * c.NB) * 8 + 16 + 256;
 }
 
 // feasible (d-planes per CTA, weight-ring depth) pairs: <= 512 TMEM columns (P accumulators per plane), <= 227 KB smem.
@@ -853,6 +734,7 @@ static int conv_tc_launch_t(const CUtensorMap& map, const ConvTcParams& p, dim3 
 struct TcLaunchArgs {
     const Net* net; int u; const __half* in; int n_pc, S, P, epi; __half* out; int cg_out_total, cg_out_off; float* prob_out;
     int side_unit; __half* side_out; int side_cg_total, side_cg_off;          // side_unit < 0: no fused side output
+    int cg_in_total;                                                          // channel groups of the input tensor when it holds more than Cin_pad/8 (0 = default)
 };
 
 static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t stream) {
@@ -862,7 +744,7 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     const TcVariant& tv = tu.v[(a.P == 2) ? 0 : 1];
     const int P = a.P, S = a.S;
     ConvTcParams p{};
-    p.S = S; p.n_pc = a.n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.pair_last = tu.pair_last; p.nv_last = tu.nv_last; p.n_cblk = tu.Cin_pad / 16; p.cg_in = tu.Cin_pad / 8;
+    p.S = S; p.n_pc = a.n_pc; p.dil = cu.dil; p.K = cu.K; p.taps = tu.taps; p.pair_last = tu.pair_last; p.nv_last = tu.nv_last; p.n_cblk = tu.Cin_pad / 16; p.cg_in = a.cg_in_total ? a.cg_in_total : tu.Cin_pad / 8;
     p.NB = cfg.NB; p.TPS = cfg.tps == 2 ? cu.K * cu.K : (cfg.tps == 1 ? cu.K : 1);
     const int AD = cfg.AD;
     const int pad = cu.dil * (cu.K / 2);
@@ -923,16 +805,16 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
 // in: blk (n_pc, P, Cin_pad/8, S^3, 8).  EPI_BLK: out blk with cg_out_total groups, written at cg_out_off.
 static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int S, int P, int epi, __half* out, int cg_out_total,
                           int cg_out_off, float* prob_out, cudaStream_t stream, int side_unit = -1, __half* side_out = nullptr,
-                          int side_cg_total = 0, int side_cg_off = 0) {
+                          int side_cg_total = 0, int side_cg_off = 0, int cg_in_total = 0) {
     TcState* st = (TcState*)net.tc;
     const ConvUnit& cu = net.units[u];
     const TcVariant& tv = st->units[u].v[(P == 2) ? 0 : 1];
-    int rc = get_encode(st);
+    int rc = tc_get_encode(st);
     if (rc != SN_OK) return rc;
     SN_CHECK_ARG(epi != EPI_FINAL || tv.n_ntiles == 1, "conv_tc: the fused merge_conv3 epilogue needs all channels in one N tile");
     int Nmax = 0;
     for (int t = 0; t < tv.n_ntiles; ++t) Nmax = std::max(Nmax, tv.nt_size[t]);
-    const TcLaunchArgs args{&net, u, in, n_pc, S, P, epi, out, cg_out_total, cg_out_off, prob_out, side_unit, side_out, side_cg_total, side_cg_off};
+    const TcLaunchArgs args{&net, u, in, n_pc, S, P, epi, out, cg_out_total, cg_out_off, prob_out, side_unit, side_out, side_cg_total, side_cg_off, cg_in_total};
 
     // one-time measurement of the tile configuration per (unit, S, mode); the timed launches rewrite the same output
     static const int env_tune = getenv("SN_TC_TUNE") ? atoi(getenv("SN_TC_TUNE")) : 1;
@@ -1017,10 +899,50 @@ constexpr int kTcMaxChunk = 128;     // pair-cubes per forward chunk: 312 MB of 
 // equal-sized chunks (80 -> 80, 200 -> 100 + 100) so that no small tail chunk runs at poor occupancy
 static int tc_chunk(int n_pc) { return n_pc <= 0 ? 0 : (int)cdiv(n_pc, cdiv(n_pc, kTcMaxChunk)); }
 
+// ---- exact mode with the w-axis Winograd units (conv_wg.cu) ----
+// Which resolution levels run their 3x3x3 units through conv_wg (level 0: conv1_x + merge units at D, 1: conv2_x at D/2, 2: conv3_x at D/4,
+// 3: the dilated conv4_x at D/4).
+struct WgLevels { bool l[4]; bool any() const { return l[0] || l[1] || l[2] || l[3]; } };
+static WgLevels wg_levels(const Net& net, int D, int P) {
+    WgLevels w;
+    w.l[0] = P == 2 && wg_supported(net, U_CONV1_1, D) && wg_supported(net, U_CONV1_2, D) && wg_supported(net, U_CONV1_3, D) &&
+             wg_supported(net, U_MERGE1, D) && wg_supported(net, U_MERGE2, D);
+    w.l[1] = P == 2 && wg_supported(net, U_CONV2_1, D / 2) && wg_supported(net, U_CONV2_2, D / 2) && wg_supported(net, U_CONV2_3, D / 2);
+    w.l[2] = P == 2 && wg_supported(net, U_CONV3_1, D / 4) && wg_supported(net, U_CONV3_2, D / 4) && wg_supported(net, U_CONV3_3, D / 4);
+    w.l[3] = P == 2 && wg_supported(net, U_CONV4_1, D / 4) && wg_supported(net, U_CONV4_2, D / 4) && wg_supported(net, U_CONV4_3, D / 4);   // dilated
+    return w;
+}
+
+// Workspace plan of the Winograd forward (halfs per pair-cube per precision plane).  Raw blk tensors feed pool / 1x1x1 / dilated / up-sample
+// consumers, "w" tensors are Winograd-domain (twice the raw size: 4 frequencies per voxel pair).  catw reuses the dead x0w|a1w|a2w region.
+struct WgPlan {
+    long long x0, a1, a2, cat, m1, W1, m1w, p1, b1, b2, s2, p1w, b1w, b2w, p2, c1, c2, s3, d1, d2, s4, p2w, c1w, c2w, c1wd, d1w, d2w, total;
+};
+static WgPlan wg_plan(int D, const WgLevels& w) {
+    const long long V = (long long)D * D * D, V2 = V / 8, V4 = V / 64;
+    WgPlan q{}; long long o = 0;
+    auto take = [&o](long long n) { const long long r = o; o += n; return r; };
+    q.x0 = take(16 * V); q.a1 = take(32 * V); q.cat = take(64 * V);
+    if (w.l[0]) { q.W1 = take(160 * V); q.m1w = take(224 * V); q.a2 = q.m1 = -1; }
+    else { q.a2 = take(32 * V); q.m1 = take(112 * V); q.W1 = q.m1w = -1; }
+    q.p1 = take(32 * V2); q.b1 = take(80 * V2); q.s2 = take(16 * V2);
+    if (w.l[1]) { q.p1w = take(64 * V2); q.b1w = take(160 * V2); q.b2w = take(160 * V2); q.b2 = -1; }
+    else { q.b2 = take(80 * V2); q.p1w = q.b1w = q.b2w = -1; }
+    q.p2 = take(80 * V4); q.c1 = take(160 * V4); q.s3 = take(16 * V4); q.s4 = take(16 * V4);
+    // conv4_x as Winograd units: 4 N tiles of 80 -> tensors of 320 channels (40 groups); c1wd = conv3_3's output in the dilated pair layout
+    if (w.l[3]) { q.d1 = take(320 * V4); q.c1wd = take(320 * V4); q.d1w = take(640 * V4); q.d2w = take(640 * V4); q.d2 = -1; }
+    else { q.d1 = take(304 * V4); q.d2 = take(304 * V4); q.c1wd = q.d1w = q.d2w = -1; }
+    if (w.l[2]) { q.p2w = take(160 * V4); q.c1w = take(320 * V4); q.c2w = take(320 * V4); q.c2 = -1; }
+    else { q.c2 = take(160 * V4); q.p2w = q.c1w = q.c2w = -1; }
+    q.total = o;
+    return q;
+}
+
 int64_t tc_workspace_bytes(const Net& net, int n_pc, int D, int mode) {
-    (void)net;
     const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
-    return align_up(tc_halfs_per_pc(D) * 2 * P * tc_chunk(n_pc), 256) + 4096;
+    const WgLevels w = wg_levels(net, D, P);
+    const long long halfs = w.any() ? wg_plan(D, w).total : tc_halfs_per_pc(D);
+    return align_up(halfs * 2 * P * tc_chunk(n_pc), 256) + 4096;
 }
 
 static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float* prob_out, __half* ws, int P, cudaStream_t st) {
@@ -1090,6 +1012,84 @@ static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float*
     return SN_OK;
 }
 
+// The forward graph with Winograd levels (exact mode).  Per level: raw blk input -> input transform (raw_to_wino) -> the 3x3x3 chain
+// in the Winograd domain (every unit's epilogue emits the next unit's transformed input) -> the last unit of the level writes raw blk for
+// its pool / side-output consumers.  Levels whose size has no Winograd instance run the direct kernels.
+static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, float* prob_out, __half* ws, const WgLevels& lv, cudaStream_t st) {
+    constexpr int P = 2;
+    const long long V = (long long)D * D * D, np = (long long)n * P;
+    const int S1 = D, S2 = D / 2, S4 = D / 4;
+    const WgPlan q = wg_plan(D, lv);
+    auto at = [&](long long off) { return off < 0 ? (__half*)nullptr : ws + off * np; };
+    __half *x0 = at(q.x0), *a1 = at(q.a1), *a2 = at(q.a2), *cat = at(q.cat), *m1 = at(q.m1), *W1 = at(q.W1), *m1w = at(q.m1w);
+    __half *p1 = at(q.p1), *b1 = at(q.b1), *b2 = at(q.b2), *s2 = at(q.s2), *p1w = at(q.p1w), *b1w = at(q.b1w), *b2w = at(q.b2w);
+    __half *p2 = at(q.p2), *c1 = at(q.c1), *c2 = at(q.c2), *s3 = at(q.s3), *d1 = at(q.d1), *d2 = at(q.d2), *s4 = at(q.s4);
+    __half *p2w = at(q.p2w), *c1w = at(q.c1w), *c2w = at(q.c2w), *c1wd = at(q.c1wd), *d1w = at(q.d1w), *d2w = at(q.d2w);
+    __half *x0w = W1, *a1w = W1 ? W1 + 32 * V * np : nullptr, *a2w = W1 ? W1 + 96 * V * np : nullptr, *catw = W1;
+    const ConvUnit* U = net.units;
+    int rc;
+#define RUN(x) do { rc = (x); if (rc != SN_OK) return rc; } while (0)
+#define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))
+#define WCONV(u, in, S, fmt, out, cgt) do { prof_begin(u, st); rc = wg_conv_launch(net, u, in, n, S, fmt, out, cgt, 0, prob_out, st); prof_end(u, st); if (rc != SN_OK) return rc; } while (0)
+    RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
+    if (lv.l[0]) {
+        RUN(raw_to_wino_launch(x0, n, 2, 0, 2, S1, x0w, 2, 0, st));
+        WCONV(U_CONV1_1, x0w, S1, WG_OUT_WINO, a1w, 4);
+        WCONV(U_CONV1_2, a1w, S1, WG_OUT_WINO, a2w, 4);
+        WCONV(U_CONV1_3, a2w, S1, WG_OUT_RAW, a1, 4);
+    } else {
+        CONV(U_CONV1_1, x0, S1, a1, 4, 0); CONV(U_CONV1_2, a1, S1, a2, 4, 0); CONV(U_CONV1_3, a2, S1, a1, 4, 0);
+    }
+    CONV(U_SIDE1, a1, S1, cat, 8, 0);                                                  // side_op1 -> concat[0:16]
+    RUN(pool_launch(a1, n, 32, P, S1, p1, st));
+    if (lv.l[1]) {
+        RUN(raw_to_wino_launch(p1, n, 4, 0, 4, S2, p1w, 4, 0, st));
+        WCONV(U_CONV2_1, p1w, S2, WG_OUT_WINO, b1w, 10);
+        WCONV(U_CONV2_2, b1w, S2, WG_OUT_WINO, b2w, 10);
+        WCONV(U_CONV2_3, b2w, S2, WG_OUT_RAW, b1, 10);
+    } else {
+        CONV(U_CONV2_1, p1, S2, b1, 10, 0); CONV(U_CONV2_2, b1, S2, b2, 10, 0); CONV(U_CONV2_3, b2, S2, b1, 10, 0);
+    }
+    CONV(U_SIDE2, b1, S2, s2, 2, 0);
+    RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, st));     // -> concat[16:32]
+    RUN(pool_launch(b1, n, 80, P, S2, p2, st));
+    if (lv.l[2]) {
+        RUN(raw_to_wino_launch(p2, n, 10, 0, 10, S4, p2w, 10, 0, st));
+        WCONV(U_CONV3_1, p2w, S4, WG_OUT_WINO, c1w, 20);
+        WCONV(U_CONV3_2, c1w, S4, WG_OUT_WINO, c2w, 20);
+        WCONV(U_CONV3_3, c2w, S4, WG_OUT_RAW, c1, 20);
+    } else {
+        CONV(U_CONV3_1, p2, S4, c1, 20, 0); CONV(U_CONV3_2, c1, S4, c2, 20, 0); CONV(U_CONV3_3, c2, S4, c1, 20, 0);
+    }
+    CONV(U_SIDE3, c1, S4, s3, 2, 0);
+    RUN(upsample_blk_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, P, S4, cat, 8, 4, st));     // -> concat[32:48]
+    if (lv.l[3]) {
+        RUN(raw_to_wino_launch(c1, n, 20, 0, 20, S4, c1wd, 20, 0, st, 2));             // dilated pairs (w, w + 2)
+        WCONV(U_CONV4_1, c1wd, S4, WG_OUT_WINO, d1w, 40);
+        do { prof_begin(U_CONV4_2, st); rc = wg_conv_launch(net, U_CONV4_2, d1w, n, S4, WG_OUT_WINO, d2w, 40, 0, nullptr, st, 40); prof_end(U_CONV4_2, st); if (rc != SN_OK) return rc; } while (0);
+        do { prof_begin(U_CONV4_3, st); rc = wg_conv_launch(net, U_CONV4_3, d2w, n, S4, WG_OUT_RAW, d1, 40, 0, nullptr, st, 40); prof_end(U_CONV4_3, st); if (rc != SN_OK) return rc; } while (0);
+        RUN(conv_tc_launch(net, U_SIDE4, d1, n, S4, P, EPI_BLK, s4, 2, 0, nullptr, st, -1, nullptr, 0, 0, 40));
+    } else {
+        CONV(U_CONV4_1, c1, S4, d1, 38, 0);
+        CONV(U_CONV4_2, d1, S4, d2, 38, 0);
+        CONV(U_CONV4_3, d2, S4, d1, 38, 0);
+        CONV(U_SIDE4, d1, S4, s4, 2, 0);
+    }
+    RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, st));     // -> concat[48:64]
+    if (lv.l[0]) {
+        RUN(raw_to_wino_launch(cat, n, 8, 0, 8, S1, catw, 8, 0, st));
+        WCONV(U_MERGE1, catw, S1, WG_OUT_WINO, m1w, 14);
+        WCONV(U_MERGE2, m1w, S1, WG_OUT_FINAL, nullptr, 0);                             // + merge_conv3 + sigmoid
+    } else {
+        CONV(U_MERGE1, cat, S1, m1, 14, 0);
+        RUN(conv_tc_launch(net, U_MERGE2, m1, n, S1, P, EPI_FINAL, nullptr, 0, 0, prob_out, st));
+    }
+#undef WCONV
+#undef CONV
+#undef RUN
+    return SN_OK;
+}
+
 int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out, void* ws, int64_t ws_bytes, int mode, cudaStream_t st) {
     const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
     const int64_t need = tc_workspace_bytes(net, n_pc, D, mode);
@@ -1099,7 +1099,9 @@ int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out,
     __half* w = (__half*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     for (int i = 0; i < n_pc; i += chunk) {
         const int n = std::min(chunk, n_pc - i);
-        int rc = tc_forward_chunk(net, X + (long long)i * 6 * V, n, D, prob_out + (long long)i * V, w, P, st);
+        const WgLevels lv = wg_levels(net, D, P);
+        int rc = lv.any() ? tc_forward_chunk_wg(net, X + (long long)i * 6 * V, n, D, prob_out + (long long)i * V, w, lv, st)
+                          : tc_forward_chunk(net, X + (long long)i * 6 * V, n, D, prob_out + (long long)i * V, w, P, st);
         if (rc != SN_OK) return rc;
     }
     return SN_OK;
@@ -1114,14 +1116,25 @@ int tc_layer_conv(const Net& net, int u, const float* in, int n, int S, float* o
     const long long vol = (long long)S * S * S;
     __half *bi = nullptr, *bo = nullptr;
     SN_CUDA(cudaMallocAsync((void**)&bi, (size_t)n * P * tu.Cin_pad * vol * 2 + 1024, st));
-    if (cudaMallocAsync((void**)&bo, (size_t)n * P * tu.Cout_pad * vol * 2 + 1024, st) != cudaSuccess) {
+    const int wg_cout_pad = std::max(tu.Cout_pad, ts->wg[u].Cout_pad);            // the Winograd variant may pad wider (300 -> 4 x 80)
+    if (cudaMallocAsync((void**)&bo, (size_t)n * P * wg_cout_pad * vol * 2 + 1024, st) != cudaSuccess) {
         cudaFreeAsync(bi, st);
         set_error("tensor-core layer call: out of device memory");
         return SN_ERR_CUDA;
     }
     int rc = pack_launch(in, n, cu.Cin, tu.Cin_pad, P, vol, bi, st);
-    if (rc == SN_OK) rc = conv_tc_launch(net, u, bi, n, S, P, EPI_BLK, bo, tu.Cout_pad / 8, 0, nullptr, st);
-    if (rc == SN_OK) rc = unpack_launch(bo, n, cu.Cout, tu.Cout_pad, P, vol, out, st);
+    if (P == 2 && wg_supported(net, u, S)) {            // Winograd instance: input transform -> conv_wg (raw blk out)
+        __half* bw = nullptr;
+        if (cudaMallocAsync((void**)&bw, (size_t)n * P * tu.Cin_pad * vol * 2 * 2 + 1024, st) != cudaSuccess) {
+            cudaFreeAsync(bi, st); cudaFreeAsync(bo, st);
+            set_error("tensor-core layer call: out of device memory");
+            return SN_ERR_CUDA;
+        }
+        if (rc == SN_OK) rc = raw_to_wino_launch(bi, n, tu.Cin_pad / 8, 0, tu.Cin_pad / 8, S, bw, tu.Cin_pad / 8, 0, st, cu.dil);
+        if (rc == SN_OK) rc = wg_conv_launch(net, u, bw, n, S, WG_OUT_RAW, bo, wg_cout_pad / 8, 0, nullptr, st);
+        cudaFreeAsync(bw, st);
+    } else if (rc == SN_OK) rc = conv_tc_launch(net, u, bi, n, S, P, EPI_BLK, bo, tu.Cout_pad / 8, 0, nullptr, st);
+    if (rc == SN_OK) rc = unpack_launch(bo, n, cu.Cout, (P == 2 && wg_supported(net, u, S)) ? wg_cout_pad : tu.Cout_pad, P, vol, out, st);
     cudaFreeAsync(bi, st); cudaFreeAsync(bo, st);
     return rc;
 }

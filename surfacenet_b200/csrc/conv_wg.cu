@@ -1,0 +1,659 @@
+// K2w -- the 3x3x3 units of SurfaceNet (nets/SurfaceNet.py:33-74) as a w-axis Winograd F(2,3) convolution on the tcgen05 tensor cores.
+//
+// Why: at the <= 1e-4 parity bound every product needs the fp16 hi/lo split (3 MMAs per product, conv_tc.cu), so the direct kernel can
+// never exceed 1/3 of the fp16 pipe; the only way to go faster at this accuracy is FEWER multiplications.  F(2,3) along w computes two
+// neighbouring outputs from four products instead of six: per output pair t (voxels w = 2t, 2t+1; inputs d0..d3 = x[2t-1..2t+2])
+//     V0 = d0 - d2, V1 = d1 + d2, V2 = d2 - d1, V3 = d1 - d3            (input transform, done by the PRODUCER of the tensor)
+//     U0 = g0, U1 = (g0+g1+g2)/2, U2 = (g0-g1+g2)/2, U3 = g2            (weights over kw, done once on the host in fp64)
+//     M_f = sum over (kd, kh, channels) of V_f * U_f                    (four 9-tap "convolutions" on the tensor cores)
+//     y[2t] = M0 + M1 + M2,  y[2t+1] = M1 - M2 - M3                     (output transform, in the epilogue registers)
+// i.e. 2/3 of the MMAs of the direct kernel for the same result.
+//
+// Data layout ("wino blk"): activations that feed a Winograd unit live in HBM ALREADY TRANSFORMED,
+//     act[n][prec][f][cg][d][h][t][8] fp16      f = frequency 0..3, t = output pair along w (S/2 per row), prec = hi / lo split of V
+// written by the epilogue of the producing unit (or by raw_to_wino_kernel): a CTA tile is 128 pairs = TH rows (h) x ALL S/2 pairs of
+// the row, so both w-neighbours of every pair sit in the same warp (one __shfl each) and the w border is the tensor border (zeros).
+// For the consumer the transformed tensor is just a (d, h, t) volume per frequency: one 4-D TMA box {8*TP, HH, HD, 2 groups} lands a
+// (d, h)-halo tile in the K-major / no-swizzle canonical layout with row m = h_local*TP + t at byte m*16 (SBO = 128 B exactly,
+// no w halo), and the 9 remaining taps (kd, kh) are descriptor start offsets, as in conv_tc.cu.
+//
+// TMEM: every frequency needs its own [main | corr] accumulator pair (2N columns, conv_tc.cu) and only 512 columns exist, so the four
+// frequencies of a tile are four consecutive passes over the K loop (each streams ITS OWN transformed tile: no operand is read twice)
+// into two alternating accumulator sets; the epilogue drains set f while set f+1 is being computed and keeps the partial output
+// transform (P0 = M0+M1+M2 so far, P1 = M1-M2-M3 so far) in registers -- 2*N values per pair, split over TWO epilogue warps per TMEM
+// lane quarter (8 epilogue warps, each N/2 columns).  After the fourth pass: folded BatchNorm + ReLU, then either the next unit's
+// input transform (neighbours by shuffle) + hi/lo split -> wino blk, or raw blk (pool / 1x1x1 consumers), or the fused merge_conv3.
+//
+// Round-toward-zero accumulation: each accumulator now sees 9*C_in/16 accumulating MMAs instead of 27*C_in/16, and all four
+// frequencies see the same number, so the relative compensation folded into the BatchNorm scale carries over unchanged.
+#include "tc_ptx.cuh"
+#include "tc_state.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace sn {
+
+constexpr int WG_THREADS = 384;        // warps: 0 A producer, 1 B producer, 2 / 3 MMA issuers (A_hi / A_lo products), 3 TMEM allocator, 4..11 epilogue
+constexpr int WG_MAX_NA = 4, WG_MAX_NB = 8;
+constexpr int WG_MAX_C = 320;          // output channels of a unit, padded (conv4: 4 x 80)
+
+struct ConvWgParams {
+    int S, n_pc, dil, n_cblk, cg_in;
+    int TP, tp_shift, TH, HH, HD;   // pairs per row (= S/2), log2(TP), rows per tile (128 / TP), halo extents in h / d
+    int NA, NB;                     // A ring stages, weight ring slots (3 taps per slot)
+    int a_prec_bytes;               // bytes of one precision plane of one A stage = 2 groups * HD*HH*TP*16
+    long long n_tiles;              // tiles_h * tiles_d * n_pc * n_ntiles; every tile = 4 frequency passes
+    int tiles_h, tiles_d, n_ntiles;
+    int nt_off[TC_MAX_NT], nt_nc[TC_MAX_NT];
+    long long nt_woff[TC_MAX_NT];
+    int pair_last, stages_per_f;    // last channel block takes its channel group at two taps as the two K halves (6 tap pairs instead of 9 taps)
+    const unsigned char* weights;   // [ntile][f][cblk][tap][kg 2][W_hi rows ; W_lo rows][8 k] fp16
+    const float* scale; const float* shift; int c_pad;    // folded BatchNorm over all c_pad output channels of the unit
+    int act, out_fmt;
+    __half* out; int cg_out_total, cg_out_off;
+    const float* w3; float scale3, shift3; float* prob_out;
+};
+
+struct WgTile { int nt, pc, d0, h0; };
+
+__device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int AD) {
+    WgTile c;
+    uint32_t q = t / (uint32_t)p.tiles_h; c.h0 = (int)(t - q * p.tiles_h) * p.TH; t = q;
+    q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * AD; t = q;
+    q = t / (uint32_t)p.n_pc; c.pc = (int)(t - q * p.n_pc);
+    c.nt = (int)q;
+    return c;
+}
+
+__device__ __forceinline__ void split_pack(const float a, const float b, uint32_t& hi, uint32_t& lo) {
+    const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+    hi = pack_h2(ah, bh);
+    lo = pack_h2(__float2half_rn(a - __half2float(ah)), __float2half_rn(b - __half2float(bh)));
+}
+
+// AD = d-planes per CTA, NH = accumulator columns per epilogue thread = N/2 (N = output channels of the N tile, padded to 16),
+// OUT = output format of the unit (WG_OUT_*): a template parameter so that only ONE epilogue variant is in the instruction stream
+// (the first version carried all three, fully unrolled over the column chunks: 150 KB of straight-line code per tile, 23 % of the
+// stall samples were instruction-cache misses and the WINO units ran at half the speed of the RAW ones).
+// Warps: 0 A producer, 1 B producer, 2 issues the A_hi MMAs, 3 the A_lo MMAs (+ TMEM allocation), 4..11 epilogue.  One warp's instruction
+// stream (~15 dependent instructions per MMA: descriptor words through R2UR) cannot feed the tensor pipe at 160 cycles per tap with a
+// single CTA per SM, hence two issuers.  Both add into the corr columns, and fp32 accumulation with truncation is not associative, so the
+// two warps hand a token back and forth (tok[0]: warp 2 may issue slot g, tok[1]: warp 3 may issue slot g): the MMAs enter the tensor
+// pipe in ONE fixed order (hi slot 0, lo slot 0, hi slot 1, ...) -> bit-reproducible results, and the pass-opening A_hi MMA
+// (accumulate = 0, it initialises the corr columns) is always ahead of the first A_lo MMA.  Each warp prepares its descriptors
+// while the other one issues; only the three UTCHMMA + the hand-off are serialised.
+template <int AD, int NH, int OUT>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p) {
+    constexpr int N = 2 * NH;
+    constexpr int TPS = 3;                                             // taps per weight slot: the three kh taps of one kd
+    constexpr int NCH = AD * NH / 8;                                   // 8-column chunks per epilogue thread
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NA = p.NA, NB = p.NB;
+    const uint32_t a_stage_bytes = (uint32_t)p.a_prec_bytes * 2;
+    const uint32_t b_slot_bytes = (uint32_t)N * 64 * TPS;              // >= 2*Nc*32 per tap
+    unsigned char* smA = smem;
+    unsigned char* smB = smem + (size_t)NA * a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)NB * b_slot_bytes);
+    uint64_t* a_full = bars, *a_empty = bars + WG_MAX_NA, *b_full = bars + 2 * WG_MAX_NA, *b_empty = b_full + WG_MAX_NB;
+    uint64_t* acc_full = b_empty + WG_MAX_NB, *acc_empty = acc_full + 2, *tok = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
+    uint32_t* pair_tbl = tmem_slot + 4 + ((warp == 3) ? 8 : 0);         // [2][8] tap-pair descriptors, private per MMA warp
+    float* zbuf = reinterpret_cast<float*>(tmem_slot + 4 + 16);         // [128][2] partial merge_conv3 sums of the upper column half
+    float* sc_s = zbuf + 256;                                           // [WG_MAX_C] folded BatchNorm scale / shift, [128] merge_conv3 weights
+    float* sh_s = sc_s + WG_MAX_C;
+    float* w3_s = sh_s + WG_MAX_C;
+    const int pad = p.dil;
+    constexpr uint32_t buf_cols = (uint32_t)(AD * 2 * N);
+    constexpr uint32_t tmem_cols = (2 * buf_cols <= 32) ? 32 : (2 * buf_cols <= 64) ? 64 : (2 * buf_cols <= 128) ? 128 : (2 * buf_cols <= 256) ? 256 : 512;
+    static_assert(2 * buf_cols <= 512, "two [main | corr] accumulator sets must fit the 512 TMEM columns");
+    const uint32_t n_tiles = (uint32_t)p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 256); }
+        mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);            // the issue-order tokens
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.c_pad; i += WG_THREADS) { sc_s[i] = p.scale[i]; sh_s[i] = p.shift[i]; }
+    if (OUT == WG_OUT_FINAL) for (int i = threadIdx.x; i < 128; i += WG_THREADS) w3_s[i] = (i < p.c_pad) ? p.w3[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== A producer: per (tile, frequency, 16-channel block) one (d, h)-halo tile of the transformed tensor, hi and lo planes =====
+        int s = 0; uint32_t ph = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const WgTile c = wg_tile(p, t, AD);
+            for (int f = 0; f < 4; ++f)
+                for (int cb = 0; cb < p.n_cblk; ++cb) {
+                    mbar_wait(&a_empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&a_full[s], a_stage_bytes);
+#pragma unroll
+                        for (int pr = 0; pr < 2; ++pr)
+                            tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
+                                        0, c.h0 - pad, c.d0 - pad, ((c.pc * 2 + pr) * 4 + f) * p.cg_in + 2 * cb);
+                    }
+                    __syncwarp();
+                    if (++s == NA) { s = 0; ph ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===== B producer: the (frequency, channel block, tap) weight stages, TPS per ring slot =====
+        const int total = p.stages_per_f / TPS;
+        int s = 0; uint32_t ph = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const WgTile c = wg_tile(p, t, AD);
+            const uint32_t slot_bytes = (uint32_t)(2 * p.nt_nc[c.nt]) * 32 * TPS;
+            for (int f = 0; f < 4; ++f) {
+                const unsigned char* wsrc = p.weights + p.nt_woff[c.nt] + (size_t)f * p.stages_per_f * (size_t)(2 * p.nt_nc[c.nt]) * 32;
+                for (int it = 0; it < total; ++it) {
+                    mbar_wait(&b_empty[s], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&b_full[s], slot_bytes);
+                        bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * slot_bytes, slot_bytes, &b_full[s]);
+                    }
+                    __syncwarp();
+                    if (++s == NB) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2 || warp == 3) {
+        // ===== MMA issuers: warp 2 = A_hi * [W_hi ; W_lo]^T -> [main | corr], warp 3 = A_lo * W_hi^T -> corr; converged warp, one elected lane =====
+        const int me = warp - 2;
+        const uint32_t ab_hi32 = 8u | (1u << 14);                            // SBO = 128 B (rows are 16 B apart, linearly), descriptor version 1
+        const uint32_t a_lbo = (uint32_t)(p.a_prec_bytes >> 5) << 16;        // the second channel group of the stage
+        const uint32_t smB16 = smem_u32(smB) >> 4;
+        const uint32_t a_stage16 = a_stage_bytes >> 4;
+        const uint32_t b_slot16 = b_slot_bytes >> 4;
+        const uint32_t plane16 = (uint32_t)(p.HH * p.TP);
+        const uint32_t kd_step = plane16 * (uint32_t)p.dil, kh_step = (uint32_t)(p.TP * p.dil);
+        const uint32_t smA16 = (smem_u32(smA) >> 4) + (me ? ((uint32_t)p.a_prec_bytes >> 4) : 0u);   // warp 3 reads the lo precision plane
+        if (p.pair_last) {                                                   // virtual tap v -> taps (2v, 2v+1) of the 9; beyond, the weights are zero
+            if (lane < 6) {
+                const int ta = min(2 * lane, 8), tb = min(2 * lane + 1, 8);
+                const uint32_t oa = (ta / 3) * kd_step + (ta % 3) * kh_step;
+                const uint32_t ob = (tb / 3) * kd_step + (tb % 3) * kh_step;
+                pair_tbl[lane] = oa | ((ob - oa) << 16);
+            }
+            __syncwarp();
+        }
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0, j = 0, g = 0;        // g = global slot counter (issue-order token phase)
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const WgTile c = wg_tile(p, t, AD);
+            const int Nc = p.nt_nc[c.nt];                                    // rows of W_hi before W_lo = column of the correction accumulator
+            const int R = 2 * Nc;
+            // D = f32, A = B = f16, K-major, M = 128; warp 2: N' = 2 Nc columns from column 0, warp 3: N columns from column Nc
+            const uint32_t idesc = (1u << 4) | ((uint32_t)((me ? N : R) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_lbo = (uint32_t)R << 16;
+            const uint32_t tapB16 = (uint32_t)(2 * R);
+            for (int f = 0; f < 4; ++f, ++j) {
+                const uint32_t buf = j & 1, use = j >> 1;
+                const uint32_t dbase = tmem_base + buf * buf_cols + (me ? (uint32_t)Nc : 0u);
+                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);                   // the epilogue has drained the previous pass of this set
+                tc_fence_after();
+                uint32_t acc_flag = me ? 1u : 0u;
+                for (int cb = 0; cb < p.n_cblk; ++cb) {
+                    mbar_wait(&a_full[sa], pha);
+                    tc_fence_after();
+                    const uint32_t a_base16 = smA16 + sa * a_stage16;
+                    const bool paired = p.pair_last && cb == p.n_cblk - 1;
+                    const int n_slots = paired ? 2 : 3;
+                    uint32_t a_kd = a_base16 | a_lbo;
+                    for (int sl = 0; sl < n_slots; ++sl, a_kd += kd_step, ++g) {
+                        mbar_wait(&b_full[sb], phb);
+                        mbar_wait(&tok[me], (g & 1) ^ (me ? 0u : 1u));  // my turn: warp 2 after lo(g-1), warp 3 after hi(g)
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t b_lo32 = (smB16 + sb * b_slot16) | b_lbo;
+#pragma unroll
+                            for (int kk = 0; kk < TPS; ++kk) {
+                                const uint32_t a_tap = paired ? a_base16 + pair_tbl[sl * TPS + kk] : a_kd + kk * kh_step;
+                                const uint64_t db = ((uint64_t)ab_hi32 << 32) | (b_lo32 + kk * tapB16);
+#pragma unroll
+                                for (int a = 0; a < AD; ++a) {
+                                    const uint64_t da = ((uint64_t)ab_hi32 << 32) | (a_tap + a * plane16);
+                                    tc_mma(dbase + (uint32_t)(a * 2 * N), da, db, idesc, acc_flag);
+                                }
+                                acc_flag = 1u;
+                            }
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[me ^ 1])) : "memory");   // pass the token
+                            tc_commit(&b_empty[sb]);
+                        }
+                        __syncwarp();
+                        acc_flag = 1u;
+                        if (++sb == NB) { sb = 0; phb ^= 1; }
+                    }
+                    if (elect_one()) tc_commit(&a_empty[sa]);
+                    __syncwarp();
+                    if (++sa == NA) { sa = 0; pha ^= 1; }
+                }
+                if (elect_one()) tc_commit(&acc_full[buf]);
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: lane quarter q = warp % 4, column half (warp - 4) / 4; row m = 32 q + lane = pair (h0 + m / TP, t = m % TP) =====
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int m = q * 32 + lane;
+        const int hl = m >> p.tp_shift, tt = m & (p.TP - 1);
+        const int S = p.S, TP = p.TP;
+        const long long vol = (long long)S * S * S, volw = vol / 2;        // voxels / pairs per channel-group plane
+        const bool first_t = tt < p.dil, last_t = tt >= TP - p.dil;         // the pair has no left / right neighbour in its row (sub-lattice)
+        float P0[AD * NH], P1[AD * NH];
+#pragma unroll
+        for (int i = 0; i < AD * NH; ++i) { P0[i] = 0.f; P1[i] = 0.f; }
+        uint32_t j = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const WgTile c = wg_tile(p, t, AD);
+            const int Nc = p.nt_nc[c.nt];
+            const int c_base = p.nt_off[c.nt] + half * NH;
+            const int h = c.h0 + hl;
+            for (int f = 0; f < 4; ++f, ++j) {
+                const uint32_t buf = j & 1, use = j >> 1;
+                // y[2t] = M0 + M1 + M2, y[2t+1] = M1 - M2 - M3 as two FMAs with exact coefficients
+                const float k0 = (f < 3) ? 1.f : 0.f;
+                const float k1 = (f == 0) ? 0.f : ((f == 1) ? 1.f : -1.f);
+                mbar_wait_sleep(&acc_full[buf], use & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int a = 0; a < AD; ++a) {
+                    const uint32_t trow = tmem_base + buf * buf_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 2 * N + half * NH);
+#pragma unroll
+                    for (int jc = 0; jc < NH; jc += 8) {
+                        uint32_t v[8], cc[8];
+                        tc_ld8(trow + jc, v);
+                        tc_ld8(trow + (uint32_t)Nc + jc, cc);
+                        tc_ld_wait();
+                        if (f == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { P0[a * NH + jc + i] = __uint_as_float(v[i]) + __uint_as_float(cc[i]); P1[a * NH + jc + i] = 0.f; }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float x = __uint_as_float(v[i]) + __uint_as_float(cc[i]);
+                                P0[a * NH + jc + i] = fmaf(k0, x, P0[a * NH + jc + i]);
+                                P1[a * NH + jc + i] = fmaf(k1, x, P1[a * NH + jc + i]);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();                                         // TMEM reads done -> the MMA warps may overwrite this set
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+            }
+            // ---- all four frequencies are in: BatchNorm + activation, then the output format of this unit.  ONE copy of the chunk code in a
+            //      rolled loop; the chunk's 16 registers are picked out of the accumulator arrays by predicated moves ----
+            float z0 = 0.f, z1 = 0.f;
+#pragma unroll 1
+            for (int ck = 0; ck < NCH; ++ck) {
+                float y0[8], y1[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { y0[i] = 0.f; y1[i] = 0.f; }
+#pragma unroll
+                for (int k = 0; k < NCH; ++k)
+                    if (k == ck) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { y0[i] = P0[k * 8 + i]; y1[i] = P1[k * 8 + i]; }
+                    }
+                const int a = ck / (NH / 8), jc = (ck - a * (NH / 8)) * 8;
+                const int d = c.d0 + a;
+                const bool ok = (d < S) && (h < S);
+                const int ch0 = c_base + jc;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float sc = sc_s[ch0 + i], sh = sh_s[ch0 + i];
+                    y0[i] = tc_act(fmaf(y0[i], sc, sh), p.act);
+                    y1[i] = tc_act(fmaf(y1[i], sc, sh), p.act);
+                }
+                const int cg = p.cg_out_off + (ch0 >> 3);
+                if (OUT == WG_OUT_FINAL) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const float w3 = w3_s[ch0 + i]; z0 = fmaf(y0[i], w3, z0); z1 = fmaf(y1[i], w3, z1); }
+                } else if (OUT == WG_OUT_WINO) {
+                    // the next unit's input transform: d0 = left neighbour's second voxel, d1, d2 = this pair, d3 = right neighbour's first voxel
+                    // (neighbour pair of the same row / sub-lattice = lane -+ dil; zero outside the row)
+                    uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        float v[2][4];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            float l = __shfl_up_sync(0xffffffffu, y1[i + e], p.dil), r = __shfl_down_sync(0xffffffffu, y0[i + e], p.dil);
+                            l = first_t ? 0.f : l; r = last_t ? 0.f : r;
+                            v[e][0] = l - y1[i + e]; v[e][1] = y0[i + e] + y1[i + e]; v[e][2] = y1[i + e] - y0[i + e]; v[e][3] = y0[i + e] - r;
+                        }
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) split_pack(v[0][f], v[1][f], hi[f][i >> 1], lo[f][i >> 1]);
+                    }
+                    if (ok) {
+                        const long long pos = ((long long)d * S + h) * TP + tt;
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) {
+                            __half* dst = p.out + ((((long long)c.pc * 2) * 4 + f) * p.cg_out_total + cg) * volw * 8 + pos * 8;
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[f][0], hi[f][1], hi[f][2], hi[f][3]);
+                            *reinterpret_cast<uint4*>(dst + 4LL * p.cg_out_total * volw * 8) = make_uint4(lo[f][0], lo[f][1], lo[f][2], lo[f][3]);
+                        }
+                    }
+                } else if (ok) {                                            // raw blk: the pair's two voxels (32 contiguous bytes when dil = 1)
+                    uint32_t hi[2][4], lo[2][4];
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        split_pack(y0[i], y0[i + 1], hi[0][i >> 1], lo[0][i >> 1]);
+                        split_pack(y1[i], y1[i + 1], hi[1][i >> 1], lo[1][i >> 1]);
+                    }
+                    const int wa = (p.dil == 1) ? 2 * tt : (tt & 1) + 4 * (tt >> 1);        // dil = 2: pair t = 2j + parity -> w = parity + 4j, + 2
+                    const long long vox = ((long long)d * S + h) * S + wa;
+                    __half* dst = p.out + (((long long)c.pc * 2) * p.cg_out_total + cg) * vol * 8 + vox * 8;
+                    __half* dlo = dst + (long long)p.cg_out_total * vol * 8;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+                    *reinterpret_cast<uint4*>(dst + 8 * p.dil) = make_uint4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+                    *reinterpret_cast<uint4*>(dlo) = make_uint4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
+                    *reinterpret_cast<uint4*>(dlo + 8 * p.dil) = make_uint4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+                }
+                if (OUT == WG_OUT_FINAL && (ck + 1) % (NH / 8) == 0) {      // plane a complete: merge_conv3 (1x1x1, C -> 1) + BatchNorm + sigmoid   SurfaceNet.py:74
+                    if (half == 1) { zbuf[2 * m] = z0; zbuf[2 * m + 1] = z1; }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (half == 0 && ok) {
+                        z0 += zbuf[2 * m]; z1 += zbuf[2 * m + 1];
+                        float2 pr;
+                        pr.x = 1.f / (1.f + expf(-fmaf(z0, p.scale3, p.shift3)));
+                        pr.y = 1.f / (1.f + expf(-fmaf(z1, p.scale3, p.shift3)));
+                        *reinterpret_cast<float2*>(p.prob_out + (long long)c.pc * vol + ((long long)d * S + h) * S + 2 * tt) = pr;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    z0 = 0.f; z1 = 0.f;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// blk raw -> wino blk: the input transform for tensors whose producer cannot emit it (pack / pool / up-sample outputs)
+// one thread per (n, group, d, h, pair): reads voxels 2t-1 .. 2t+2 (hi + lo), writes the four frequencies (hi, lo)
+__global__ void __launch_bounds__(256)
+raw_to_wino_kernel(const __half* __restrict__ in, int cg_in_total, int cg_in_off, int cg_count, int S, int dil, long long total,
+                   __half* __restrict__ out, int cg_out_total, int cg_out_off) {
+    const int TP = S / 2;
+    const long long vol = (long long)S * S * S, volw = vol / 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {                                         // i over (n, g, d, h, t)
+        const int t = (int)(i % TP);
+        const long long row = i / TP;                                       // (n, g, d, h)
+        const long long dh = row % ((long long)S * S);
+        const int g = (int)((row / ((long long)S * S)) % cg_count);
+        const long long n = row / ((long long)S * S * cg_count);
+        const __half* src = in + ((n * 2) * cg_in_total + cg_in_off + g) * vol * 8 + (dh * S) * 8;
+        const long long prec_in = (long long)cg_in_total * vol * 8;
+        float d[4][8];
+#pragma unroll
+        const int wa = (dil == 1) ? 2 * t : (t & 1) + 4 * (t >> 1);            // dil = 2: pair t = 2j + parity -> voxels parity + 4j, + 2
+        for (int k = 0; k < 4; ++k) {
+            const int w = wa + (k - 1) * dil;                                   // d0..d3 = x[wa - dil], x[wa], x[wa + dil], x[wa + 2 dil]
+            if (w >= 0 && w < S) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + (long long)w * 8));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + prec_in + (long long)w * 8));
+                const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 fa = __half22float2(ha[e]), fb = __half22float2(hb[e]);
+                    d[k][2 * e] = fa.x + fb.x; d[k][2 * e + 1] = fa.y + fb.y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[k][e] = 0.f;
+            }
+        }
+        const long long pos = dh * TP + t;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+                float v[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float d0 = d[0][e + u], d1 = d[1][e + u], d2 = d[2][e + u], d3 = d[3][e + u];
+                    v[u] = (f == 0) ? d0 - d2 : (f == 1) ? d1 + d2 : (f == 2) ? d2 - d1 : d1 - d3;
+                }
+                split_pack(v[0], v[1], hi[e >> 1], lo[e >> 1]);
+            }
+            __half* dst = out + (((n * 2) * 4 + f) * cg_out_total + cg_out_off + g) * volw * 8 + pos * 8;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dst + 4LL * cg_out_total * volw * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
+int raw_to_wino_launch(const __half* in_raw, int n, int cg_in_total, int cg_in_off, int cg_count, int S, __half* out_wino, int cg_out_total,
+                       int cg_out_off, cudaStream_t stream, int dil) {
+    const long long total = (long long)n * cg_count * S * S * (S / 2);
+    if (!total) return SN_OK;
+    SN_CHECK_ARG(S % (2 * dil) == 0 && (dil == 1 || dil == 2), "raw_to_wino: size %d / dilation %d", S, dil);
+    const int blocks = (int)std::min<long long>(cdiv(total, 256), 148 * 16);
+    raw_to_wino_kernel<<<blocks, 256, 0, stream>>>(in_raw, cg_in_total, cg_in_off, cg_count, S, dil, total, out_wino, cg_out_total, cg_out_off);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+static int pad16w(int c) { return (int)align_up(c, 16); }
+
+static bool wg_unit_enabled(int u) {
+    // SN_WG=0 switches the Winograd path off; SN_WG_UNITS=<bit mask over unit ids> restricts it (debugging aid)
+    static const int env_on = getenv("SN_WG") ? atoi(getenv("SN_WG")) : 1;
+    static const long long env_mask = getenv("SN_WG_UNITS") ? strtoll(getenv("SN_WG_UNITS"), nullptr, 0) : -1LL;
+    return env_on && ((env_mask >> u) & 1);
+}
+
+int wg_prepare(Net& net) {
+    TcState* st = (TcState*)net.tc;
+    static const double G[4][3] = {{1, 0, 0}, {0.5, 0.5, 0.5}, {0.5, -0.5, 0.5}, {0, 0, 1}};
+    for (int u = 0; u < kNumUnits; ++u) {
+        const ConvUnit& cu = net.units[u];
+        if ((cu.kind != UNIT_CONV && cu.kind != UNIT_DIL) || cu.K != 3) continue;   // conv1_x .. conv3_x, the dilated conv4_x, the two merge units
+        WgUnit& wu = st->wg[u];
+        wu.Cin_pad = pad16w(cu.Cin);
+        wu.n_cblk = wu.Cin_pad / 16;
+        wu.pair_last = (cu.Cin % 16 >= 1 && cu.Cin % 16 <= 8) ? 1 : 0;
+        wu.stages_per_f = (wu.n_cblk - 1) * 9 + (wu.pair_last ? 6 : 9);
+        // N tiling: two [main | corr] accumulator sets of 2N columns each in 512 TMEM columns -> N <= 112.  Equal tiles of one of the
+        // instantiated widths (32 / 80 / 112), whichever pads the unit least: 32 -> 32, 80 -> 80, 100 -> 112, 160 -> 2 x 80, 300 -> 4 x 80
+        int nsz = 0;
+        for (int cand : {32, 80, 112}) {
+            const int nt = (int)cdiv(cu.Cout, cand);
+            if (nt <= TC_MAX_NT && (!nsz || nt * cand < wu.n_ntiles * nsz || (nt * cand == wu.n_ntiles * nsz && cand > nsz))) { nsz = cand; wu.n_ntiles = nt; }
+        }
+        if (!nsz) continue;
+        wu.Cout_pad = nsz * wu.n_ntiles;
+        // transformed weights U_f[co][ci][kd*3+kh] in fp64, common power-of-two pre-scale (hi and lo normal fp16 numbers)
+        std::vector<double> U((size_t)4 * cu.Cout * cu.Cin * 9);
+        double umax = 0.0;
+        for (int co = 0; co < cu.Cout; ++co)
+            for (int ci = 0; ci < cu.Cin; ++ci)
+                for (int t2 = 0; t2 < 9; ++t2)
+                    for (int f = 0; f < 4; ++f) {
+                        double s = 0.0;
+                        for (int kw = 0; kw < 3; ++kw) s += G[f][kw] * (double)cu.h_w[((size_t)co * cu.Cin + ci) * 27 + t2 * 3 + kw];
+                        U[(((size_t)f * cu.Cout + co) * cu.Cin + ci) * 9 + t2] = s;
+                        umax = std::max(umax, fabs(s));
+                    }
+        int e = 0;
+        if (umax > 0.0) { e = (int)floor(log2(1024.0 / umax)); e = std::max(-14, std::min(24, e)); }
+        const double wscale = ldexp(1.0, e);
+        const float inv = ldexpf(1.f, -e);
+        size_t bytes = 0;
+        for (int t = 0; t < wu.n_ntiles; ++t) {
+            wu.nt_size[t] = nsz; wu.nt_off[t] = t * nsz;
+            const int real = std::max(0, std::min(nsz, cu.Cout - wu.nt_off[t]));
+            wu.nt_nc[t] = std::max((int)align_up(real, 8), nsz / 2);
+            wu.nt_woff[t] = (long long)bytes;
+            bytes += (size_t)4 * wu.stages_per_f * (2 * wu.nt_nc[t]) * 32;
+        }
+        std::vector<__half> h(bytes / 2, __float2half_rn(0.f));
+        for (int t = 0; t < wu.n_ntiles; ++t) {
+            const int Nc = wu.nt_nc[t], R = 2 * Nc;
+            for (int f = 0; f < 4; ++f) {
+                __half* base = h.data() + wu.nt_woff[t] / 2 + (size_t)f * wu.stages_per_f * R * 16;
+                for (int cb = 0; cb < wu.n_cblk; ++cb) {
+                    const bool paired = wu.pair_last && cb == wu.n_cblk - 1;
+                    for (int tap = 0; tap < (paired ? 6 : 9); ++tap)                     // paired: `tap` is the virtual tap (pair index)
+                        for (int nn = 0; nn < nsz; ++nn)
+                            for (int kk = 0; kk < 16; ++kk) {
+                                const int co = wu.nt_off[t] + nn;
+                                const int ci = paired ? cb * 16 + kk % 8 : cb * 16 + kk;   // paired: both K halves are channel group 2*cb
+                                const int rtap = paired ? 2 * tap + kk / 8 : tap;        //         at taps 2v and 2v+1
+                                if (co >= cu.Cout || ci >= cu.Cin || rtap >= 9) continue;
+                                const float wv = (float)(U[(((size_t)f * cu.Cout + co) * cu.Cin + ci) * 9 + rtap] * wscale);
+                                const __half hi = __float2half_rn(wv);
+                                const __half lo = __float2half_rn(wv - __half2float(hi));
+                                const size_t stage = ((size_t)cb * 9 + tap) * R * 16;
+                                const size_t idx = (size_t)(kk / 8) * R * 8 + (size_t)(nn / 8) * 64 + (nn % 8) * 8 + (kk % 8);
+                                base[stage + idx] = hi;
+                                base[stage + (size_t)Nc * 8 + idx] = lo;
+                            }
+                }
+            }
+        }
+        SN_CUDA(cudaMalloc((void**)&wu.w, bytes));
+        SN_CUDA(cudaMemcpy(wu.w, h.data(), bytes, cudaMemcpyHostToDevice));
+        // round-toward-zero compensation (conv_tc.cu:tc_prepare): n_acc accumulating MMAs into every frequency's main accumulator
+        const double kRzLoss = 0.5 * 0.70 * ldexp(1.0, -23) * 0.5;
+        static const int env_comp = getenv("SN_TC_RZCOMP") ? atoi(getenv("SN_TC_RZCOMP")) : 1;
+        static const double env_scale = getenv("SN_WG_RZSCALE") ? atof(getenv("SN_WG_RZSCALE")) : 1.0;
+        const double n_acc = (double)(wu.n_cblk - 1) * 9 + (wu.pair_last ? 5 : 9);
+        const float comp = env_comp ? (float)(1.0 + env_scale * kRzLoss * n_acc) : 1.f;
+        std::vector<float> sc(wu.Cout_pad, 0.f), sh(wu.Cout_pad, 0.f);
+        for (int c = 0; c < cu.Cout; ++c) { sc[c] = cu.h_scale[c] * inv * comp; sh[c] = cu.h_shift[c]; }
+        SN_CUDA(cudaMalloc((void**)&wu.scale, sc.size() * 4));
+        SN_CUDA(cudaMalloc((void**)&wu.shift, sh.size() * 4));
+        SN_CUDA(cudaMemcpy(wu.scale, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
+        SN_CUDA(cudaMemcpy(wu.shift, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice));
+        wu.on = true;
+    }
+    return SN_OK;
+}
+
+void wg_destroy(Net& net) {
+    TcState* st = (TcState*)net.tc;
+    if (!st) return;
+    for (int u = 0; u < kNumUnits; ++u) { cudaFree(st->wg[u].w); cudaFree(st->wg[u].scale); cudaFree(st->wg[u].shift); st->wg[u] = WgUnit(); }
+}
+
+// supported geometry: a tile is 128 pairs = (128 / TP) full rows of TP = S/2 pairs, TP in {8, 16, 32}
+bool wg_supported(const Net& net, int u, int S) {
+    const TcState* st = (const TcState*)net.tc;
+    return st && st->wg[u].on && wg_unit_enabled(u) && (S == 16 || S == 32 || S == 64);
+}
+
+struct WgCfg { int AD, NA, NB; size_t smem; };
+
+static size_t wg_smem_bytes(int S, int N, int dil, int AD, int NA, int NB) {
+    const int TP = S / 2, TH = 128 / TP;
+    const size_t a_stage = (size_t)2 * 2 * (AD + 2 * dil) * (TH + 2 * dil) * TP * 16;
+    return (size_t)NA * a_stage + (size_t)NB * N * 64 * 3 + (2 * WG_MAX_NA + 2 * WG_MAX_NB + 6) * 8 + 16 + 64 + 128 * 2 * 4 +
+           (2 * WG_MAX_C + 128) * 4 + 64;
+}
+
+static WgCfg wg_config(int S, int N, int dil) {
+    static const int env_ad = getenv("SN_WG_AD") ? atoi(getenv("SN_WG_AD")) : 0;
+    static const int env_na = getenv("SN_WG_NA") ? atoi(getenv("SN_WG_NA")) : 0;
+    static const int env_nb = getenv("SN_WG_NB") ? atoi(getenv("SN_WG_NB")) : 0;
+    WgCfg c;
+    c.AD = (N == 32) ? 4 : 1;                                               // 2 sets * AD * 2N columns <= 512
+    if (env_ad && N == 32 && (env_ad == 2 || env_ad == 4)) c.AD = env_ad;
+    c.AD = std::min(c.AD, S);
+    const size_t budget = 220 * 1024;
+    c.NA = env_na ? std::max(2, std::min(WG_MAX_NA, env_na)) : 3;
+    while (c.NA > 2 && wg_smem_bytes(S, N, dil, c.AD, c.NA, 2) > budget) --c.NA;
+    c.NB = 2;
+    while (c.NB < WG_MAX_NB && wg_smem_bytes(S, N, dil, c.AD, c.NA, c.NB + 1) <= budget) ++c.NB;
+    if (env_nb) c.NB = std::max(2, std::min(c.NB, env_nb));
+    c.smem = wg_smem_bytes(S, N, dil, c.AD, c.NA, c.NB);
+    return c;
+}
+
+template <int AD, int NH, int OUT>
+static int wg_launch_t(const CUtensorMap& map, const ConvWgParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, NH, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+        attr_set = true;
+    }
+    conv_wg_kernel<AD, NH, OUT><<<grid, WG_THREADS, smem, stream>>>(map, p);
+    return SN_OK;
+}
+
+int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S, int out_fmt, __half* out, int cg_out_total, int cg_out_off,
+                   float* prob_out, cudaStream_t stream, int cg_in_total) {
+    TcState* st = (TcState*)net.tc;
+    const ConvUnit& cu = net.units[u];
+    const WgUnit& wu = st->wg[u];
+    SN_CHECK_ARG(wg_supported(net, u, S), "conv_wg: unit %s at S=%d has no Winograd instance", kUnits[u].name, S);
+    SN_CHECK_ARG(out_fmt != WG_OUT_FINAL || (wu.n_ntiles == 1 && u == U_MERGE2), "conv_wg: the fused merge_conv3 epilogue belongs to merge_conv2");
+    int rc = tc_get_encode(st);
+    if (rc != SN_OK) return rc;
+    if (!n_pc) return SN_OK;
+    const int N = wu.nt_size[0];
+    const WgCfg cfg = wg_config(S, N, cu.dil);
+    ConvWgParams p{};
+    p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.n_cblk = wu.n_cblk; p.cg_in = cg_in_total ? cg_in_total : wu.Cin_pad / 8;
+    p.TP = S / 2; p.tp_shift = (p.TP == 8) ? 3 : (p.TP == 16 ? 4 : 5); p.TH = 128 / p.TP;
+    p.HH = p.TH + 2 * cu.dil; p.HD = cfg.AD + 2 * cu.dil;
+    p.NA = cfg.NA; p.NB = cfg.NB;
+    p.a_prec_bytes = 2 * p.HD * p.HH * p.TP * 16;
+    p.tiles_h = S / p.TH; p.tiles_d = (int)cdiv(S, cfg.AD); p.n_ntiles = wu.n_ntiles;
+    p.n_tiles = (long long)n_pc * p.tiles_d * p.tiles_h * wu.n_ntiles;
+    for (int t = 0; t < TC_MAX_NT; ++t) { p.nt_off[t] = wu.nt_off[t]; p.nt_nc[t] = wu.nt_nc[t]; p.nt_woff[t] = wu.nt_woff[t]; }
+    p.pair_last = wu.pair_last; p.stages_per_f = wu.stages_per_f;
+    p.weights = wu.w; p.scale = wu.scale; p.shift = wu.shift; p.c_pad = wu.Cout_pad; p.act = cu.act; p.out_fmt = out_fmt;
+    p.out = out; p.cg_out_total = cg_out_total; p.cg_out_off = cg_out_off;
+    p.w3 = st->w3; p.scale3 = st->scale3; p.shift3 = st->shift3; p.prob_out = prob_out;
+    SN_CHECK_ARG(p.n_tiles <= 0x7fffffff && p.stages_per_f % 3 == 0 && p.cg_in * 8 >= wu.Cin_pad && wu.Cout_pad <= WG_MAX_C &&
+                 (out_fmt == WG_OUT_FINAL || cg_out_off + wu.Cout_pad / 8 <= cg_out_total), "conv_wg: bad tiling (tiles=%lld)", p.n_tiles);
+    SN_CHECK_ARG(cfg.smem <= 227 * 1024, "conv_wg: shared memory %zu", cfg.smem);
+
+    CUtensorMap map;
+    const cuuint64_t gdim[4] = {(cuuint64_t)8 * p.TP, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)n_pc * 2 * 4 * p.cg_in};
+    const cuuint64_t gstr[3] = {(cuuint64_t)p.TP * 16, (cuuint64_t)S * p.TP * 16, (cuuint64_t)S * S * p.TP * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)(8 * p.TP), (cuuint32_t)p.HH, (cuuint32_t)p.HD, 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = st->encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)in_wino, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for Winograd unit %s, S=%d", (int)cr, kUnits[u].name, S); return SN_ERR_CUDA; }
+
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; SN_CUDA(cudaGetDevice(&dev)); SN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    dim3 grid((unsigned)std::min<long long>(p.n_tiles, n_sm));               // persistent, one CTA per SM (TMEM: 512 columns)
+    const size_t smem = std::max(cfg.smem, (size_t)(227 * 1024 / 2) + 1);     // never two CTAs per SM: the second would spin in tcgen05.alloc
+    rc = SN_ERR_INVALID;
+#define SN_WG_CASE(ad, nh) if (cfg.AD == ad && N == 2 * nh) rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nh, WG_OUT_WINO>(map, p, grid, smem, stream) \
+                                                                                             : wg_launch_t<ad, nh, WG_OUT_RAW>(map, p, grid, smem, stream)
+    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112) rc = wg_launch_t<1, 56, WG_OUT_FINAL>(map, p, grid, smem, stream); }
+    else { SN_WG_CASE(4, 16); SN_WG_CASE(2, 16); SN_WG_CASE(1, 40); SN_WG_CASE(1, 56); }
+#undef SN_WG_CASE
+    if (rc != SN_OK) { if (rc == SN_ERR_INVALID) set_error("conv_wg: no kernel instance for AD=%d N=%d", cfg.AD, N); return rc; }
+    SN_LAUNCHED();
+    return SN_OK;
+}
+
+}  // namespace sn

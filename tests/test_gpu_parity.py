@@ -190,6 +190,40 @@ def test_conv_units(torch_cuda, net, params, name, S, mode):
     assert err <= CONV_TOL[mode] * scale, "%s: max-abs %g" % (name, err)
 
 
+# sizes with a Winograd F(2,3) instance (csrc/conv_wg.cu: S in {16, 32, 64}; rows of S/2 output pairs, N tiles 32 / 80 / 112)
+CONV_CASES_WG = [("conv1_1", 16), ("conv1_2", 32), ("conv1_3", 16), ("conv2_1", 16), ("conv2_2", 32), ("conv3_1", 16), ("conv3_2", 16),
+                 ("merge_conv", 16), ("merge_conv2", 16), ("merge_conv2", 32), ("conv1_2", 64), ("conv4_1", 16), ("conv4_2", 16),
+                 ("conv4_3", 32)]
+
+
+@pytest.mark.parametrize("name,S", CONV_CASES_WG)
+def test_conv_units_winograd(torch_cuda, net, params, name, S):
+    """The 3x3x3 units (dilated conv4_x included) at the sizes the exact mode runs as w-axis Winograd F(2,3) (4 frequency passes,
+    output transform in the epilogue registers), vs torch-CPU fp32; same tolerance as the direct kernel.  n = 3 samples so that the persistent tile loop
+    wraps around the accumulator double buffer with an odd tile count."""
+    import torch
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import _lib, weights
+    names = [u[0] for u in weights.UNITS]
+    u = names.index(name)
+    _, kind, cin, cout, k = weights.UNITS[u]
+    n = 3 if S < 64 else 1
+    rs = np.random.RandomState(100 + u)
+    x = _layer_in(rs, n, cin, S)
+    with torch.no_grad():
+        ref = so.conv_bn(torch.from_numpy(x), params, weights.unit_index()[name], "relu", dilated=(kind == "dil")).numpy()
+    xd = torch.from_numpy(x).cuda()
+    out = torch.full((n, cout, S, S, S), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_net_layer_conv(net.handle, u, _lib.ptr(xd), n, S, _lib.ptr(out), _lib.MODES["exact"], _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all(), "%s: unwritten / non-finite outputs" % name
+    err = np.abs(o - ref).max()
+    scale = max(1.0, np.abs(ref).max())
+    print("%s S=%d winograd: max-abs %.3g (ref max %.3g)" % (name, S, err, scale))
+    assert err <= CONV_TOL["exact"] * scale, "%s: max-abs %g" % (name, err)
+
+
 @pytest.mark.parametrize("unit,f,S", [("up2", 2, 5), ("up3", 4, 3), ("up4", 4, 4)])
 def test_upsample_units(torch_cuda, net, params, unit, f, S):
     import torch

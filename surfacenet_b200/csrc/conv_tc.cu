@@ -327,18 +327,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                     } else if (ok) {
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
-                            __half hi[8], lo[8];
+                            uint32_t hi[4], lo[4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                hi[i] = __float2half_rn(y[8 * g + i]);
-                                lo[i] = __float2half_rn(y[8 * g + i] - __half2float(hi[i]));
-                            }
+                            for (int i = 0; i < 4; ++i) split_pack(y[8 * g + 2 * i], y[8 * g + 2 * i + 1], hi[i], lo[i]);
                             const int cg = p.cg_out_off + ((c_base + jc) >> 3) + g;
                             __half* dst = p.out + (((long long)c.pc * P) * p.cg_out_total + cg) * vol * 8 + vox * 8;
-                            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-                            if (P == 2)
-                                *reinterpret_cast<uint4*>(dst + (long long)p.cg_out_total * vol * 8) =
-                                    make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            if (P == 2) *reinterpret_cast<uint4*>(dst + (long long)p.cg_out_total * vol * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                 }
@@ -347,19 +342,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
                 if (SIDE && ok) {
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
-                        __half hi[8], lo[8];
+                        float sv[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int o = 8 * g + i;
-                            const float sv = 1.f / (1.f + expf(-fmaf(sacc[o], __ldg(p.side_scale + o), __ldg(p.side_shift + o))));
-                            hi[i] = __float2half_rn(sv);
-                            lo[i] = __float2half_rn(sv - __half2float(hi[i]));
+                            sv[i] = 1.f / (1.f + expf(-fmaf(sacc[o], __ldg(p.side_scale + o), __ldg(p.side_shift + o))));
                         }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_pack(sv[2 * i], sv[2 * i + 1], hi[i], lo[i]);
                         __half* dst = p.side_out + (((long long)c.pc * P) * p.side_cg_total + p.side_cg_off + g) * vol * 8 + vox * 8;
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-                        if (P == 2)
-                            *reinterpret_cast<uint4*>(dst + (long long)p.side_cg_total * vol * 8) =
-                                make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        if (P == 2) *reinterpret_cast<uint4*>(dst + (long long)p.side_cg_total * vol * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
             }
@@ -378,30 +372,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const ConvTcParams p)
 // ------------------------------------------------------------------------------------------------
 // small blk-format kernels (HBM-bound)
 
-// fp32 NCDHW (n, C, vol) -> blk (n, P, cg, vol, 8); channels >= C are zero
-__global__ void pack_blk_kernel(const float* __restrict__ x, int C, int cg, int P, long long vol, long long total, __half* __restrict__ out) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {                     // i over (n, g, voxel)
-        const long long vox = i % vol;
-        const int g = (int)((i / vol) % cg);
-        const long long n = i / (vol * cg);
-        __half hi[8], lo[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int c = g * 8 + k;
-            const float v = (c < C) ? __ldg(x + (n * C + c) * vol + vox) : 0.f;
-            hi[k] = __float2half_rn(v);
-            lo[k] = __float2half_rn(v - __half2float(hi[k]));
-        }
-        __half* dst = out + ((n * P) * cg + g) * vol * 8 + vox * 8;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-        if (P == 2)
-            *reinterpret_cast<uint4*>(dst + (long long)cg * vol * 8) =
-                make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
-    }
-}
-
 __device__ __forceinline__ void load_blk8(const __half* src, long long prec_stride, int P, float (&v)[8]) {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
     const __half2* ha = reinterpret_cast<const __half2*>(&a);
@@ -416,12 +386,29 @@ __device__ __forceinline__ void load_blk8(const __half* src, long long prec_stri
 }
 
 __device__ __forceinline__ void store_blk8(__half* dst, long long prec_stride, int P, const float (&v)[8]) {
-    __half hi[8], lo[8];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { hi[k] = __float2half_rn(v[k]); lo[k] = __float2half_rn(v[k] - __half2float(hi[k])); }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-    if (P == 2)
-        *reinterpret_cast<uint4*>(dst + prec_stride) = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+    for (int k = 0; k < 4; ++k) split_pack(v[2 * k], v[2 * k + 1], hi[k], lo[k]);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (P == 2) *reinterpret_cast<uint4*>(dst + prec_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// fp32 NCDHW (n, C, vol) -> blk (n, P, cg, vol, 8); channels >= C are zero
+__global__ void pack_blk_kernel(const float* __restrict__ x, int C, int cg, int P, long long vol, long long total, __half* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {                     // i over (n, g, voxel)
+        const long long vox = i % vol;
+        const int g = (int)((i / vol) % cg);
+        const long long n = i / (vol * cg);
+        float v8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            v8[k] = (c < C) ? __ldg(x + (n * C + c) * vol + vox) : 0.f;
+        }
+        store_blk8(out + ((n * P) * cg + g) * vol * 8 + vox * 8, (long long)cg * vol * 8, P, v8);
+    }
 }
 
 // blk -> fp32 NCDHW (first C channels)

@@ -65,12 +65,6 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
     return c;
 }
 
-__device__ __forceinline__ void split_pack(const float a, const float b, uint32_t& hi, uint32_t& lo) {
-    const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-    hi = pack_h2(ah, bh);
-    lo = pack_h2(__float2half_rn(a - __half2float(ah)), __float2half_rn(b - __half2float(bh)));
-}
-
 // AD = d-planes per CTA, NH = accumulator columns per epilogue thread = N/2 (N = output channels of the N tile, padded to 16),
 // OUT = output format of the unit (WG_OUT_*): a template parameter so that only ONE epilogue variant is in the instruction stream
 // (the first version carried all three, fully unrolled over the column chunks: 150 KB of straight-line code per tile, 23 % of the
@@ -264,7 +258,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 // y[2t] = M0 + M1 + M2, y[2t+1] = M1 - M2 - M3 as two FMAs with exact coefficients
                 const float k0 = (f < 3) ? 1.f : 0.f;
                 const float k1 = (f == 0) ? 0.f : ((f == 1) ? 1.f : -1.f);
-                mbar_wait_sleep(&acc_full[buf], use & 1);
+                mbar_wait_sleep(&acc_full[buf], use & 1, 64);             // a late drain start delays the MMA warps two passes later
                 tc_fence_after();
 #pragma unroll
                 for (int a = 0; a < AD; ++a) {

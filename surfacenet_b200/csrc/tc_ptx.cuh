@@ -27,7 +27,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 // long waits (epilogue warps waiting for the whole main loop): back off so the spinning warps do not steal issue slots
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 256) {
     uint32_t done;
     while (true) {
         asm volatile(
@@ -37,7 +37,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
             "selp.u32 %0, 1, 0, p;\n\t"
             "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(256);
+        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -102,6 +102,17 @@ __device__ __forceinline__ float tc_act(float y, int act) {
     if (act == SN_ACT_RELU) return fmaxf(y, 0.f);
     if (act == SN_ACT_SIGMOID) return 1.f / (1.f + expf(-y));
     return y;
+}
+
+// fp16 hi / lo split of two fp32 values, packed conversions: cvt.rn.f16x2.f32 is one ALU-pipe instruction (F2FP.PACK_AB), the scalar
+// __float2half_rn is an F2F on the quarter-rate conversion unit (measured: 64 F2F per 8-channel chunk were the top stall of the Winograd
+// epilogue).  hi = fp16(x), lo = fp16(x - hi).
+__device__ __forceinline__ void split_pack(const float a, const float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {

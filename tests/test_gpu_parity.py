@@ -250,7 +250,8 @@ def test_upsample_micro_cases_device(torch_cuda, net):
     x = torch.zeros(1, 1, 2, 2, 2); x[0, 0, :, 0, 0] = torch.tensor([1.0, 2.0])
     for unit, f, want in (("up3", 4, [1, 2 / 3, 1.0, 4 / 3, 2, 4 / 3, 2 / 3, 0]), ("up2", 2, [1, 1.5, 2, 1.0])):
         out = torch.zeros((1, 1, 2 * f, 2 * f, 2 * f), dtype=torch.float32, device="cuda")
-        _lib.check(_lib.lib.sn_net_layer_upsample(net.handle, names.index(unit), _lib.ptr(x.cuda()), 1, 1, 2, _lib.ptr(out), 1, 0,
+        xd = x.cuda()
+        _lib.check(_lib.lib.sn_net_layer_upsample(net.handle, names.index(unit), _lib.ptr(xd), 1, 1, 2, _lib.ptr(out), 1, 0,
                                                   _lib.stream_ptr()))
         assert np.allclose(out[0, 0, :, 0, 0].cpu().numpy(), want, atol=1e-6)
 
@@ -262,12 +263,14 @@ def test_maxpool_and_fusion(torch_cuda):
     rs = np.random.RandomState(0)
     x = torch.from_numpy(rs.standard_normal((2, 5, 6, 6, 6)).astype(np.float32))
     out = torch.empty((2, 5, 3, 3, 3), dtype=torch.float32, device="cuda")
-    _lib.check(_lib.lib.sn_maxpool2(_lib.ptr(x.cuda()), 2, 5, 6, _lib.ptr(out), _lib.stream_ptr()))
+    xd = x.cuda()                                           # keep the device tensors alive across the raw-pointer calls
+    _lib.check(_lib.lib.sn_maxpool2(_lib.ptr(xd), 2, 5, 6, _lib.ptr(out), _lib.stream_ptr()))
     assert torch.equal(out.cpu(), F.max_pool3d(x, 2, 2))
     p = torch.from_numpy(rs.rand(3, 4, 100).astype(np.float32))
     w = torch.from_numpy((rs.rand(3, 4) + 0.1).astype(np.float32))
     fo = torch.empty((3, 100), dtype=torch.float32, device="cuda")
-    _lib.check(_lib.lib.sn_fuse_weighted_average(_lib.ptr(p.cuda()), _lib.ptr(w.cuda()), 3, 4, 100, _lib.ptr(fo), _lib.stream_ptr()))
+    pd, wd = p.cuda(), w.cuda()
+    _lib.check(_lib.lib.sn_fuse_weighted_average(_lib.ptr(pd), _lib.ptr(wd), 3, 4, 100, _lib.ptr(fo), _lib.stream_ptr()))
     ref = (p * (w / w.sum(1, keepdim=True))[:, :, None]).sum(1)
     assert (fo.cpu() - ref).abs().max() <= 1e-6
 

@@ -1,9 +1,12 @@
 #!/bin/bash
-# quick regression + bench: tests of the tensor-core paths, then the default bench line (no CPU leg)
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "winograd or forward or infer_batch or conv_units or maxpool or upsample" > gpurun_out/quick_tests.log 2>&1
+# quick regression + bench with hang guards: one Winograd unit first (a deadlocked kernel must not eat the GPU budget)
+timeout 150 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "winograd and conv1_1" > gpurun_out/quick_first.log 2>&1
+rc=$?; echo "first exit $rc"; tail -3 gpurun_out/quick_first.log
+if [ $rc -ne 0 ]; then exit 1; fi
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "winograd or forward or infer_batch or conv_units or maxpool or upsample" > gpurun_out/quick_tests.log 2>&1
 echo "tests exit $?" >> gpurun_out/quick_tests.log
 grep -E "passed|failed|exit|^FAILED" gpurun_out/quick_tests.log | tail -8
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err
+timeout 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err
 python - <<'PY'
 import json
 try:

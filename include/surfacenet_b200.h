@@ -47,6 +47,10 @@ int         sn_version(void);
 /* number of kernels this library has launched since load / since the last reset (bench: gpu_launches) */
 int64_t     sn_launch_count(void);
 void        sn_launch_count_reset(void);
+/* which convolution kernels ran since the last sn_launch_count_reset: counts[0] = CUDA-core fp32 units (mode fp32), counts[1] = direct
+ * tcgen05 units (conv_tc.cu), counts[2] = Winograd F(2,3) tcgen05 units (conv_wg.cu).  Lets a caller / test verify that the path it asked
+ * for is the path that ran (there is no silent fallback between them). */
+void        sn_conv_path_counts(int64_t counts[3]);
 
 /* Per-launch timing of the convolution units with CUDA events on the launching stream (the reference
  * has only commented-out time.time() probes: utils/rayPooling.py:69-138).  enable(1) clears and starts

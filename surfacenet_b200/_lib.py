@@ -40,6 +40,7 @@ SIGNATURES = {
     "sn_version": (_i, []),
     "sn_launch_count": (_i64, []),
     "sn_launch_count_reset": (None, []),
+    "sn_conv_path_counts": (None, [C.POINTER(C.c_int64)]),
     "sn_profile_enable": (None, [_i]),
     "sn_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_int64), _i]),
     "sn_perspective_proj": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p, _p]),

@@ -12,6 +12,7 @@ namespace sn {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int64_t> g_conv_path[3];     // launches of fp32 / direct tensor-core / Winograd tensor-core conv units
 
 #define SN_CHECK_ARG(cond, ...)                         \
     do {                                                \

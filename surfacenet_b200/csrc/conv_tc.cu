@@ -785,6 +785,7 @@ static int conv_tc_launch_cfg(const TcLaunchArgs& a, TileCfg cfg, cudaStream_t s
     SN_TC_CASE(1, 2); SN_TC_CASE(2, 2); SN_TC_CASE(3, 2); SN_TC_CASE(4, 2);
 #undef SN_TC_CASE
     if (rc != SN_OK) return rc;
+    g_conv_path[1].fetch_add(1, std::memory_order_relaxed);
     SN_LAUNCHED();
     return SN_OK;
 }

@@ -677,6 +677,7 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     else { SN_WG_CASE(4, 32); SN_WG_CASE(2, 32); SN_WG_CASE(1, 80); SN_WG_CASE(1, 112); }
 #undef SN_WG_CASE
     if (rc != SN_OK) { if (rc == SN_ERR_INVALID) set_error("conv_wg: no kernel instance for AD=%d N=%d", cfg.AD, N); return rc; }
+    g_conv_path[2].fetch_add(1, std::memory_order_relaxed);
     SN_LAUNCHED();
     return SN_OK;
 }

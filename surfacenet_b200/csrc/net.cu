@@ -7,6 +7,7 @@ namespace sn {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+std::atomic<int64_t> g_conv_path[3];
 
 void set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -81,7 +82,8 @@ using namespace sn;
 extern "C" const char* sn_last_error(void) { return g_err; }
 extern "C" int sn_version(void) { return 100; }
 extern "C" int64_t sn_launch_count(void) { return g_launches.load(); }
-extern "C" void sn_launch_count_reset(void) { g_launches.store(0); }
+extern "C" void sn_launch_count_reset(void) { g_launches.store(0); for (auto& c : g_conv_path) c.store(0); }
+extern "C" void sn_conv_path_counts(int64_t counts[3]) { for (int i = 0; i < 3; ++i) counts[i] = g_conv_path[i].load(); }
 
 extern "C" void sn_profile_enable(int on) {
     for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }

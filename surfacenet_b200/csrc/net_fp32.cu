@@ -122,6 +122,7 @@ int conv_fp32_launch(const ConvUnit& u, const float* in, int n, int S, float* ou
         conv3d_fp32_kernel<1><<<grid, CV_THREADS, smem, st>>>(in, u.w_fp32, u.scale, u.shift, out, u.Cin, u.Cin_pad, u.Cout, S, u.dil, u.act, C_total, c_off);
     }
     prof_end(u.id, st);
+    g_conv_path[0].fetch_add(1, std::memory_order_relaxed);
     SN_LAUNCHED();
     return SN_OK;
 }

@@ -333,6 +333,105 @@ def test_forward_s64_full_size_exact(torch_cuda, params, cams):
     assert e_f <= PROB_TOL and e_u <= PROB_TOL
 
 
+# ---- parity as a distribution: weight seeds x view-pair counts x cubes --------------------------------------
+def _survey_case(cams, params, D, n_cubes, n_vp, seed):
+    """-> (max-abs fused, max-abs unfused) of the exact mode vs the torch-CPU fp32 oracle on CVC input."""
+    from oracle import surfacenet_oracle as so
+    from surfacenet_b200 import SurfaceNet
+    X, *_ = _real_like_X(cams, D, n_cubes=n_cubes, n_vp=n_vp, seed=1000 + 17 * seed + n_vp)
+    w = (np.random.RandomState(seed * 7 + n_vp).rand(n_cubes, n_vp) + 0.1).astype(np.float32)
+    fused_o, unf_o = so.nViewPair_SurfaceNet_fn(X, params, w if n_vp > 1 else None, N_vp=n_vp, chunk=4 if D <= 32 else 1)
+    _, fn = SurfaceNet.SurfaceNet_inference(n_vp, params)                 # the documented drop-in call: default mode
+    fused, unf = fn(X, w) if n_vp > 1 else fn(X)
+    return float(np.abs(fused - fused_o).max()), float(np.abs(unf - unf_o).max())
+
+
+SURVEY_64 = [(0, 1), (1, 1), (2, 1), (3, 1), (4, 1), (1, 5), (0, 8), (3, 8)]        # (weight seed, N_vp) at the BASELINE cube size, 1 cube each
+
+
+@pytest.mark.parametrize("seed,n_vp", SURVEY_64)
+def test_parity_distribution_s64(torch_cuda, cams, seed, n_vp):
+    """Five synthetic weight sets (BatchNorm calibrated on real DTU CVCs per seed: tests/golden/make_synth_bn.py), N_vp in {1, 5, 8},
+    64^3 cubes: fused AND unfused probabilities within 1e-4 of the oracle (nets/layers.py:321-339 fusion, SurfaceNet.py:126,343-357)."""
+    from surfacenet_b200 import weights
+    e_f, e_u = _survey_case(cams, weights.synthetic_params(seed), 64, 1, n_vp, seed)
+    print("s=64 seed %d N_vp %d: max-abs fused %.3g unfused %.3g" % (seed, n_vp, e_f, e_u))
+    assert e_f <= PROB_TOL and e_u <= PROB_TOL
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("n_vp", [5, 8])
+def test_parity_distribution_s32_four_cubes(torch_cuda, cams, seed, n_vp):
+    """Same survey at s=32 with 4 random cubes per case (mixed path: Winograd levels at 32 / 16, direct kernels at 8)."""
+    from surfacenet_b200 import weights
+    e_f, e_u = _survey_case(cams, weights.synthetic_params(seed), 32, 4, n_vp, seed)
+    print("s=32 seed %d N_vp %d x 4 cubes: max-abs fused %.3g unfused %.3g" % (seed, n_vp, e_f, e_u))
+    assert e_f <= PROB_TOL and e_u <= PROB_TOL
+
+
+@pytest.mark.parametrize("name,S", [("merge_conv2", 32), ("conv4_2", 16), ("conv2_2", 17), ("conv4_1", 7)])
+@pytest.mark.parametrize("kind", ["all_positive", "zero_mean", "one_sided_large"])
+def test_accumulation_truncation_extremes(torch_cuda, params, name, S, kind):
+    """tcgen05 accumulates with round-toward-zero; the expected loss is folded back into the BatchNorm scale (kRzLoss, conv_tc.cu /
+    conv_wg.cu).  Bound that statistical compensation on adversarial operands: all-positive weights and activations (every partial sum
+    grows monotonically: the largest possible truncation bias), zero-mean operands (no bias to compensate), and large one-sided
+    activations; Winograd units (S in {16,32}) and direct units (odd S), against an fp64 evaluation."""
+    import torch
+    import torch.nn.functional as F
+    from surfacenet_b200 import SurfaceNet, _lib, weights
+    names = [u[0] for u in weights.UNITS]
+    u = names.index(name)
+    _, ukind, cin, cout, k = weights.UNITS[u]
+    i0 = weights.unit_index()[name]
+    rs = np.random.RandomState(31 + u)
+    p2 = [a.copy() for a in params]
+    W = p2[i0]
+    x = rs.standard_normal((1, cin, S, S, S)).astype(np.float32) * 1.5
+    if kind == "all_positive":
+        p2[i0] = np.abs(W); x = np.abs(x)
+    elif kind == "one_sided_large":
+        x = (np.abs(x) * 40.0 + 10.0).astype(np.float32)
+    # identity BatchNorm so that the pre-activation itself is compared: beta 0, gamma 1, mean 0, inv_std 1
+    p2[i0 + 1][:] = 0; p2[i0 + 2][:] = 1; p2[i0 + 3][:] = 0; p2[i0 + 4][:] = 1
+    net2 = SurfaceNet.Net(p2)
+    Wt = torch.from_numpy(p2[i0]).double()
+    dil = ukind == "dil"
+    if dil:
+        Wt = Wt.permute(1, 0, 2, 3, 4).contiguous()
+    ref = torch.relu(F.conv3d(torch.from_numpy(x).double(), Wt, padding=(2 if dil else 1) * (k // 2), dilation=2 if dil else 1)).numpy()
+    xd = torch.from_numpy(x).cuda()
+    out = torch.full((1, cout, S, S, S), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib.sn_net_layer_conv(net2.handle, u, _lib.ptr(xd), 1, S, _lib.ptr(out), _lib.MODES["exact"], _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - ref).max()
+    scale = max(1.0, np.abs(ref).max())
+    print("%s S=%d %s: max-abs %.3g / ref max %.3g = %.3g" % (name, S, kind, err, scale, err / scale))
+    # measured on B200: zero-mean <= 2.9e-6, one-sided activations <= 3.6e-6 (what a BatchNorm + ReLU network feeds its units), all-positive
+    # weights AND activations 4.5e-6 (Winograd, 63 MMAs per accumulator) .. 2.0e-5 (direct kernel, 270 MMAs): the worst case of the
+    # statistical compensation stays inside the per-unit tolerance of the exact mode
+    tol = CONV_TOL["exact"] if kind == "all_positive" else 5e-6
+    assert err <= tol * scale, "%s %s: relative error %g" % (name, kind, err / scale)
+
+
+def test_documented_import_swap_runs_the_tensor_core_kernels(torch_cuda, params, cams):
+    """`from surfacenet_b200 import SurfaceNet` + SurfaceNet_inference(N, model) with NO mode argument must run
+    the tcgen05 kernels (conv_wg / conv_tc), not the CUDA-core fp32 cross-check path."""
+    from surfacenet_b200 import SurfaceNet, _lib
+    X, *_ = _real_like_X(cams, 16, n_cubes=1, n_vp=1, seed=5)
+    _, fn = SurfaceNet.SurfaceNet_inference(1, params)
+    import ctypes as C
+    _lib.lib.sn_launch_count_reset()
+    fn(X)
+    counts = (C.c_int64 * 3)()
+    _lib.lib.sn_conv_path_counts(counts)
+    assert counts[0] == 0 and counts[1] + counts[2] >= 18 and counts[2] >= 5, "default call ran fp32/direct/winograd = %s" % list(counts)
+    _, fn32 = SurfaceNet.SurfaceNet_inference(1, params, mode="fp32")
+    _lib.lib.sn_launch_count_reset()
+    fn32(X)
+    _lib.lib.sn_conv_path_counts(counts)
+    assert counts[0] >= 18 and counts[1] == 0 and counts[2] == 0
+
+
 def test_forward_fast_mode_reports_error(torch_cuda, params, cams):
     """Single-pass fp16 operands: explicitly NOT a parity mode; its error is measured and bounded loosely."""
     from oracle import surfacenet_oracle as so

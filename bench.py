@@ -11,8 +11,9 @@ A "step" = one batch of the hot loop of main_reconstruct.py:132-162 per GPU.  Wo
 BASELINE.json configs[2], the 64^3 configuration the headline target is quoted on; largest single-GPU
 config): 16 cubes of 64^3 x 5 view pairs per GPU, weighted fusion + ray pooling, DTU cal18 cameras,
 synthetic uint8 1200x1600 images, synthetic calibrated weights.  Weak scaling: every rank owns its own
-16 cubes; the per-cube fused probability (f32) and votes (u8) volumes are all-gathered ONCE at the
-end of the step, inside the timed region.
+16 cubes; the per-cube float16 prediction and the votes (u8) volumes -- what the consumer reads, utils/sparseCubes.py:115 --
+are all-gathered ONCE per step, inside the timed region; the float16 gather runs under the ray-pool kernels.
+At 8 GPUs (or with --c4-shard) the line also carries "c4_shard": one BASELINE configs[3] shard (64 cubes x 8 view pairs per GPU).
 
 value  = fused surface-probability voxels / s, whole job, inputs resident in HBM (device timed, max over ranks)
 e2e    = same metric through HotPath.infer_batch_host: pinned HOST per-batch arguments in, fused f32 +
@@ -200,25 +201,31 @@ def run_gpu(args, wl):
     hp = pipeline.HotPath(net, scene, mode=mode)
     pairs, xyz, resol, w = make_inputs(wl, rank)
     d_pairs, d_xyz, d_resol, d_w = (torch.from_numpy(a).to(dev) for a in (pairs, xyz, resol, w))
-    gathered_p = torch.empty((world * B, 1, D, D, D), dtype=torch.float32, device=dev) if world > 1 else None
+    from surfacenet_b200 import rayPooling
+    # multi-GPU: what the consumer of the per-cube volumes reads is the float16 prediction (utils/sparseCubes.py:115) and the votes: gather
+    # THOSE (3 B / voxel instead of 5).  The float16 gather is issued right after the cast and runs on NCCL's stream under the ray-pool kernels.
+    gathered_p = torch.empty((world * B, D, D, D), dtype=torch.float16, device=dev) if world > 1 else None
     gathered_v = torch.empty((world * B, D, D, D), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    rp_ws = torch.empty(int(_lib.lib.sn_raypool_workspace_bytes(wl["cubes"], n_vp, D)), dtype=torch.uint8, device=dev)
 
-    def gather(fused, votes):
-        if world > 1:                                                       # ONE all-gather per output at the end of the step
-            dist.all_gather_into_tensor(gathered_p, fused)
-            dist.all_gather_into_tensor(gathered_v, votes)
+    def device_step(d_pairs, d_xyz, d_resol, d_w, g_p, g_v):
+        if world == 1:
+            return hp.infer_batch(d_pairs, d_xyz, d_resol, d_w, D, want_unfused=False, ray_pool=True)
+        out = hp.infer_batch(d_pairs, d_xyz, d_resol, d_w, D, want_unfused=False, ray_pool=False)
+        h1 = dist.all_gather_into_tensor(g_p, out["pred16"], async_op=True)
+        out["votes"] = rayPooling.votes_device(out["pred16"], d_pairs, d_xyz, d_resol, scene.P, scene.n_views, hp.min_prob, workspace=rp_ws)
+        h2 = dist.all_gather_into_tensor(g_v, out["votes"], async_op=True)
+        h1.wait(); h2.wait()
+        return out
 
     def step_device():
-        out = hp.infer_batch(d_pairs, d_xyz, d_resol, d_w, D, want_unfused=False, ray_pool=True)
-        gather(out["fused"], out["votes"])
-        return out
+        return device_step(d_pairs, d_xyz, d_resol, d_w, gathered_p, gathered_v)
 
     def step_host():
-        out = hp.infer_batch_host(pairs, xyz, resol, w, D, want_fused=True, ray_pool=True)
-        if world > 1:
-            gather(torch.from_numpy(out["fused"]).to(dev, non_blocking=True), torch.from_numpy(out["votes"]).to(dev, non_blocking=True))
-        return out
+        # the host-buffer entry returns THIS rank's cubes in host memory; the scene-level exchange of the (sparse) results happens once per
+        # scene in reconstruct.reconstruct_cubes(gather=True), not per batch -- no device re-upload of host results
+        return hp.infer_batch_host(pairs, xyz, resol, w, D, want_fused=True, ray_pool=True)
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -268,6 +275,20 @@ def run_gpu(args, wl):
     if sampler:
         sampler.stop()
 
+    # BASELINE configs[3] (512 cubes x 8 view pairs over 8 GPUs): one shard = 64 cubes x 8 pairs per rank, timed next to the c3 line on
+    # the multi-GPU runs (and on request with --c4-shard); same step, same gather
+    c4 = None
+    if (world >= 8 or args.c4_shard) and args.workload == "c3":
+        w4 = WORKLOADS["c4"]
+        p4, x4, r4, ww4 = make_inputs(w4, rank)
+        dd = [torch.from_numpy(a).to(dev) for a in (p4, x4, r4, ww4)]
+        g4p = torch.empty((world * w4["cubes"], D, D, D), dtype=torch.float16, device=dev) if world > 1 else None
+        g4v = torch.empty((world * w4["cubes"], D, D, D), dtype=torch.uint8, device=dev) if world > 1 else None
+        rp_ws = torch.empty(int(_lib.lib.sn_raypool_workspace_bytes(w4["cubes"], w4["n_vp"], D)), dtype=torch.uint8, device=dev)
+        ms4, l4, _ = timed(lambda: device_step(dd[0], dd[1], dd[2], dd[3], g4p, g4v), max(2, args.steps // 4), 1)
+        c4 = {"workload": w4["name"], "cubes_per_gpu": w4["cubes"], "view_pairs": w4["n_vp"], "ms_per_step": ms4, "comm_nranks": world,
+              "value": world * w4["cubes"] * V / (ms4 * 1e-3), "unit": "voxels/s",
+              "pair_voxels_per_s": world * w4["cubes"] * w4["n_vp"] * V / (ms4 * 1e-3), "gpu_launches": l4}
     if rank == 0:
         tc_peak, hbm_peak, peak_src = peaks()
         macs = unit_macs_per_voxel()
@@ -301,7 +322,7 @@ def run_gpu(args, wl):
             "data": "synthetic",
             "config": {"workload": wl["name"], "mode": mode, "cubes_per_gpu": B, "view_pairs": n_vp, "cube_D": D,
                        "l2": "256 MiB flush write between timed steps; per-step activations exceed L2",
-                       "parallelism": "cube-sharded x%d, one all-gather of prob+votes per step" % world},
+                       "parallelism": "cube-sharded x%d, one all-gather each of the float16 prediction (overlapped with ray pooling) and the votes per step" % world},
             "pair_voxels_per_s": world * pair_vox_step / (ms_dev * 1e-3),
             "path_tflops": FLOP_PER_PAIR_VOXEL * world * pair_vox_step / (ms_dev * 1e-3) / 1e12,
             "e2e": {"value": fused_vox / (ms_e2e * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d_e2e, "d2h_bytes_per_step": d2h_e2e,
@@ -310,16 +331,19 @@ def run_gpu(args, wl):
                            "what": "numpy in -> per-cube sparse lists out (adds colour fusion + centre-crop/threshold compaction on the GPU; no all-gather)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel, merge_conv2 launch (3x3x3 100->100 + fused merge_conv3/sigmoid), %d launches/step" % (cnt_u[dom] // args.steps),
+            "roofline": {"bound": "tensor", "kernel": "conv_wg_kernel<1,112,FINAL>, merge_conv2 launch (3x3x3 100->100 as w-axis Winograd F(2,3) + fused merge_conv3/sigmoid), %d launches/step" % (cnt_u[dom] // args.steps),
                          "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s", "frac": achieved / tc_peak, "traffic": traffic,
                          "peak_source": peak_src, "flop_per_launch": dom_flop_launch, "ms_per_launch": dom_ms_launch,
                          "kernel_share_of_step": ms_u[dom] / args.steps / ms_dev,
                          "all_conv_units": {"launches_per_step": conv_launches // args.steps, "tflops": conv_tflops, "frac": conv_tflops / tc_peak,
                                             "share_of_step": conv_ms / args.steps / ms_dev},
-                         # merge_conv2, exact: 3 products; columns 208 + 112 per (block, tap) for 3 x 100 real ones; K elements 6 x 27 x 16 + 18 x 16 for 27 x 100
-                         "exact_mode_ceiling_frac": (1.0 / 3.0) * (300.0 / 320.0) * (2700.0 / 2880.0) if mode in ("exact", "tc_exact") else None,
+                         # merge_conv2, exact + Winograd F(2,3) along w: algorithmic 27 x 100 x 100 MAC per voxel; executed per 256-voxel tile 4 frequencies
+                         # x 60 (channel block, tap) stages x (208 + 112) columns x 128 rows x 16 K = 614,400 MAC per voxel -> 0.4395 of the fp16 pipe
+                         "exact_mode_ceiling_frac": 270000.0 / 614400.0 if mode in ("exact", "tc_exact") else None,
                          "per_unit": per_unit},
         }
+        if c4 is not None:
+            line["c4_shard"] = c4
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             cpu_reference_step(dict(wl, D=16), params, cams, imgs, 1, threads)        # warm torch's thread pool
@@ -492,6 +516,8 @@ def run_post(args):
                              "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": post_traffic(dom),
                              "peak_source": peak_src, "bytes_per_call": bytes_call[dom], "ms_per_call": dom_ms,
                              "calls_ms_per_step": {k: parts[k] for k in parts}, "calls_per_step": n_calls}}
+        if c4 is not None:
+            line["c4_shard"] = c4
         if world == 1 and not args.no_cpu_baseline:
             small = util.sparse_scene((2, 2, 2), POST_D, seed=50, floaters=40, thick=0.05)
             n_small = sum(x.shape[0] for x in small["ijk_list"])
@@ -607,6 +633,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["post", "simnet"])
     ap.add_argument("--mode", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-shard", action="store_true", help="also time one BASELINE configs[3] shard (64 cubes x 8 view pairs per GPU); always on at 8 GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "post":

@@ -92,16 +92,12 @@ def __readCameraPO_as_np_DTU__(cameraPO_file):
 
 
 def __readCameraPOs_as_np_Middlebury__(cameraPO_file, viewList):
-    """utils/camera.py:26-53: `name K(9) R(9) t(3)` per line after a count line; P = K [R | t]; line n <-> view n (1-based)."""
-    with open(cameraPO_file) as f:
-        lines = f.readlines()
-    cameraPOs = np.empty((len(lines), 3, 4)).astype(np.float64)
-    for _n, _l in enumerate(lines):
-        if _n == 0:
-            continue
-        _params = np.array(_l.strip().split(' ')[1:], dtype=np.float64)
-        cameraPOs[_n] = np.dot(_params[:9].reshape((3, 3)), np.c_[_params[9:18].reshape((3, 3)), _params[18:].reshape((3, 1))])
-    return cameraPOs[list(viewList)]
+    """utils/camera.py:26-53.  Middlebury `*_par.txt`: a count line, then one line per image `name k11..k33 r11..r33 t1 t2 t3`;
+    P = K [R | t].  Row n of the table is view n (1-based: row 0, the count line, is never selected)."""
+    table = np.genfromtxt(cameraPO_file, skip_header=1, usecols=range(1, 22), dtype=np.float64).reshape(-1, 21)
+    K, R, t = table[:, :9].reshape(-1, 3, 3), table[:, 9:18].reshape(-1, 3, 3), table[:, 18:21].reshape(-1, 3, 1)
+    P = np.matmul(K, np.concatenate([R, t], axis=2))                        # (N_images, 3, 4)
+    return P[np.asarray(list(viewList), dtype=np.int64) - 1]                 # view n <-> data row n - 1
 
 
 def readCameraPOs_as_np(datasetFolder, datasetName, poseNamePattern, model, viewList):

@@ -35,6 +35,8 @@ WORKLOADS = {                          # cubes per GPU, view pairs, cube side
     "c2": dict(cubes=64, n_vp=5, D=32, name="synthetic-image DTU-camera s=32 cubes, 64 cubes x 5 view-pairs per GPU (BASELINE configs[1])"),
     "c3": dict(cubes=16, n_vp=5, D=64, name="synthetic-image DTU-camera s=64 cubes, 16 cubes x 5 weighted view-pairs + rayPooling per GPU (BASELINE configs[2])"),
     "c4": dict(cubes=64, n_vp=8, D=64, name="synthetic 64^3 cubes, 64 cubes x 8 view-pairs per GPU (BASELINE configs[3] = 512 cubes on 8 GPUs)"),
+    # whole-scene workload (own GPU arm, run_c5); the reference arm times one cube x 3 pairs of the same size per step
+    "c5": dict(cubes=16, n_vp=3, D=64, name="Middlebury dinoSparseRing views 7-12, whole-scene reconstruction, s=64, N_vp=3, cube-sharded (BASELINE configs[4])"),
 }
 
 
@@ -362,6 +364,78 @@ def run_gpu(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------------
+def run_c5(args, wl):
+    """BASELINE configs[4]: Middlebury dinoSparseRing (real images + calibration, tests/golden/real), views 7-12, s=64 cubes, N_vp=3,
+    params.py:174-182.  One step = the whole reconstruct.reconstruction call: cube grid (2,016 cubes) -> early rejection (similarityNet)
+    -> view-pair selection -> SurfaceNet inference on this rank's share of the cube batches -> gather of the sparse lists -> fixed
+    threshold + cross-cube denoising.  value = fused voxels of the cubes that survive early rejection / s (whole job)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from surfacenet_b200 import _lib, camera, image, reconstruct, similarityNet, weights
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    real = os.path.join(REPO, "tests", "golden", "real")
+    views = list(range(7, 13))
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        imgs = image.readImages(real, "dinoSparseRing/dinoSR0#.png", views)
+    P = camera.readCameraPOs_as_np(real, "Middlebury", "dinoSparseRing/dinoSR_par.txt", "dinoSparseRing", views)
+    BB = np.array([(-0.061897, 0.010897), (-0.018874, 0.068227), (-0.057845, 0.015495)], dtype=np.float32)
+    params = weights.synthetic_params(1)
+    sp = similarityNet.synthetic_params(0)
+    sp[28] = np.array([[-0.02]], np.float32); sp[29] = np.array([-0.4], np.float32)
+    D = wl["D"]
+
+    def step():
+        return reconstruct.reconstruction(imgs, P, BB, np.float32(0.00025), wl["n_vp"], params, sp, outputFolder=None, cube_D=D, batch_size=16,
+                                          tau=0.7, gamma=0.8, model="dinoSparseRing", rank=rank, world_size=world)
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(max(1, min(args.warmup, 1))):
+        out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    _lib.lib.sn_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    if rank == 0:
+        n_valid = int(out["validCubes"].sum())
+        vox = n_valid * D ** 3
+        line = {"metric": "fused surface-probability voxels/sec, whole-scene reconstruction (early rejection + selection + CVC + SurfaceNet + rayPooling + sparsify + denoise)",
+                "value": vox / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16x2-split operands, f32 accumulate", "data": "real images (reference fixtures), synthetic weights",
+                "config": {"workload": wl["name"], "cubes_in_grid": int(out["validCubes"].size), "cubes_after_early_rejection": n_valid,
+                           "sparse_voxels": int(sum(len(x) for x in out["result"][0])), "view_pairs": wl["n_vp"], "cube_D": D,
+                           "parallelism": "cube batches dealt round-robin to %d ranks, all_gather_object of the sparse lists" % world},
+                "gpu_launches": int(_lib.lib.sn_launch_count()) // steps, "clocks": sampler.window(t0, t1) if sampler else None,
+                "e2e": {"value": vox / (ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": int(sum(i.nbytes for i in imgs)), "d2h_bytes_per_step": int(sum(len(x) for x in out["result"][0]) * 8),
+                        "what": "the step IS the host-facing call: numpy images / cameras in, sparse numpy lists out"}}
+        print(json.dumps(line))
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
 # "next" row N4: the post-processing of the scene's sparse cubes (main_reconstruct.py:170-173 + utils/adapthresh.py:91-178)
 POST_GRID, POST_D, POST_ITERS = (8, 8, 4), 52, 8          # 256 half-overlapping 52^3 centre cubes, params.py:107,113
 
@@ -643,6 +717,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.workload == "c5":
+        run_c5(args, wl)
     else:
         run_gpu(args, wl)
 

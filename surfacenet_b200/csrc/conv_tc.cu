@@ -514,6 +514,89 @@ upsample_blk_kernel(const __half* __restrict__ in, const float* __restrict__ W, 
     }
 }
 
+// Same up-sampler, writing the WINOGRAD-DOMAIN layout of conv_wg.cu directly (groups [cg_off, cg_off + cg_in) of a wino blk tensor with
+// cg_total groups at F*S): one thread per output PAIR (voxels w = 2t, 2t+1) of one row; lanes = consecutive pairs of the row, so the
+// two neighbour voxels the input transform needs come from lane -+ 1 by shuffle (zero at the row ends).  Saves the raw concat tensor
+// round trip (write 1.3 GB + read + transform per group and launch at 80 pair-cubes of 64^3).
+template <int F, int K>
+__global__ void __launch_bounds__(256)
+upsample_wino_kernel(const __half* __restrict__ in, const float* __restrict__ W, int cg_in, int S,
+                     __half* __restrict__ out, int cg_total, int cg_off) {
+    constexpr int C0 = K / 2, NT = (K + F - 1) / F;
+    __shared__ float sW[K * K * K];
+    for (int i = threadIdx.x; i < K * K * K; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    const int So = S * F, TP = So / 2;                                       // TP divides 32 or is a multiple of it (So in {16, 32, 64, ...})
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = idx < So * TP;                                       // whole rows per warp: inactive lanes only in a trailing partial block
+    const int oh = active ? idx / TP : 0, tt = active ? idx - oh * TP : 0;
+    const long long n = blockIdx.z;
+    const long long vol = (long long)S * S * S, volw = (long long)So * So * TP;
+    const bool first_t = tt == 0, last_t = tt == TP - 1;
+    for (int od = blockIdx.y * UP_PLANES; od < min(So, (int)(blockIdx.y + 1) * UP_PLANES); ++od) {
+        int src[2][NT * NT * NT];
+        float wt[2][NT * NT * NT];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const int ow = 2 * tt + e2;
+            const int td0 = (C0 - od) & (F - 1), th0 = (C0 - oh) & (F - 1), tw0 = (C0 - ow) & (F - 1);
+#pragma unroll
+            for (int jd = 0; jd < NT; ++jd)
+#pragma unroll
+                for (int jh = 0; jh < NT; ++jh)
+#pragma unroll
+                    for (int jw = 0; jw < NT; ++jw) {
+                        const int td = td0 + jd * F, th = th0 + jh * F, tw = tw0 + jw * F;
+                        const int pd = od + td - C0, ph = oh + th - C0, pw = ow + tw - C0;
+                        const bool ok = td < K && th < K && tw < K && pd >= 0 && pd < So && ph >= 0 && ph < So && pw >= 0 && pw < So;
+                        const int e = (jd * NT + jh) * NT + jw;
+                        src[e2][e] = ok ? ((pd / F) * S + ph / F) * S + pw / F : -1;
+                        wt[e2][e] = ok ? sW[(td * K + th) * K + tw] : 0.f;
+                    }
+        }
+        const long long pos = ((long long)od * So + oh) * TP + tt;
+        for (int g = 0; g < cg_in; ++g) {
+            const __half* base = in + ((n * 2) * cg_in + g) * vol * 8;
+            float y[2][8];
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) y[e2][q] = 0.f;
+#pragma unroll
+                for (int e = 0; e < NT * NT * NT; ++e) {
+                    if (src[e2][e] < 0) continue;
+                    float v[8];
+                    load_blk8(base + (long long)src[e2][e] * 8, (long long)cg_in * vol * 8, 2, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) y[e2][q] = fmaf(wt[e2][e], v[q], y[e2][q]);
+                }
+            }
+            // input transform of the consumer (conv_wg.cu): V0 = x[2t-1] - x[2t+1], V1 = x[2t] + x[2t+1], V2 = x[2t+1] - x[2t], V3 = x[2t] - x[2t+2]
+            uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                float v[2][4];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float l = __shfl_up_sync(0xffffffffu, y[1][q + e], 1), r = __shfl_down_sync(0xffffffffu, y[0][q + e], 1);
+                    l = first_t ? 0.f : l; r = last_t ? 0.f : r;
+                    v[e][0] = l - y[1][q + e]; v[e][1] = y[0][q + e] + y[1][q + e]; v[e][2] = y[1][q + e] - y[0][q + e]; v[e][3] = y[0][q + e] - r;
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f) split_pack(v[0][f], v[1][f], hi[f][q >> 1], lo[f][q >> 1]);
+            }
+            if (active) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    __half* dst = out + (((n * 2) * 4 + f) * cg_total + cg_off + g) * volw * 8 + pos * 8;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[f][0], hi[f][1], hi[f][2], hi[f][3]);
+                    *reinterpret_cast<uint4*>(dst + 4LL * cg_total * volw * 8) = make_uint4(lo[f][0], lo[f][1], lo[f][2], lo[f][3]);
+                }
+            }
+        }
+    }
+}
+
 static inline int ew_blocks(long long total) { return (int)std::min<long long>(cdiv(total, 256), 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -876,6 +959,19 @@ static int upsample_blk_launch(const __half* in, const float* W, int k, int f, i
     SN_LAUNCHED();
     return SN_OK;
 }
+// the same into a Winograd-domain tensor (exact mode, P = 2); the rows of So/2 pairs must tile the warps: So in {16, 32, 64}
+static int upsample_wino_launch(const __half* in, const float* W, int k, int f, int n, int Cpad, int S, __half* out, int cg_total,
+                                int cg_off, cudaStream_t st) {
+    const int So = S * f, cg_in = Cpad / 8;
+    if (!n || !S) return SN_OK;
+    SN_CHECK_ARG((k == 3 && f == 2) || (k == 5 && f == 4), "upsample: only (k=3, x2) and (k=5, x4) exist in SurfaceNet (nets/layers.py:383)");
+    SN_CHECK_ARG((So == 16 || So == 32 || So == 64) && n <= 65535, "upsample (Winograd layout): unsupported size %d", So);
+    dim3 grid((unsigned)cdiv((long long)So * (So / 2), 256), (unsigned)cdiv(So, UP_PLANES), (unsigned)n);
+    if (f == 2) upsample_wino_kernel<2, 3><<<grid, 256, 0, st>>>(in, W, cg_in, S, out, cg_total, cg_off);
+    else upsample_wino_kernel<4, 5><<<grid, 256, 0, st>>>(in, W, cg_in, S, out, cg_total, cg_off);
+    SN_LAUNCHED();
+    return SN_OK;
+}
 
 // halfs of workspace per pair-cube (per precision plane)
 static long long tc_halfs_per_pc(int D) {
@@ -1039,7 +1135,9 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
         CONV(U_CONV2_1, p1, S2, b1, 10, 0); CONV(U_CONV2_2, b1, S2, b2, 10, 0); CONV(U_CONV2_3, b2, S2, b1, 10, 0);
     }
     CONV(U_SIDE2, b1, S2, s2, 2, 0);
-    RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, st));     // -> concat[16:32]
+    // level 0 as Winograd units: the up-samplers write the Winograd-domain concat tensor directly (catw aliases the dead x0w|a1w|a2w region)
+    if (lv.l[0]) RUN(upsample_wino_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, S2, catw, 8, 2, st));
+    else RUN(upsample_blk_launch(s2, U[U_UP2].up_W, 3, 2, n, 16, P, S2, cat, 8, 2, st));     // -> concat[16:32]
     RUN(pool_launch(b1, n, 80, P, S2, p2, st));
     if (lv.l[2]) {
         RUN(raw_to_wino_launch(p2, n, 10, 0, 10, S4, p2w, 10, 0, st));
@@ -1050,7 +1148,8 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
         CONV(U_CONV3_1, p2, S4, c1, 20, 0); CONV(U_CONV3_2, c1, S4, c2, 20, 0); CONV(U_CONV3_3, c2, S4, c1, 20, 0);
     }
     CONV(U_SIDE3, c1, S4, s3, 2, 0);
-    RUN(upsample_blk_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, P, S4, cat, 8, 4, st));     // -> concat[32:48]
+    if (lv.l[0]) RUN(upsample_wino_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, S4, catw, 8, 4, st));
+    else RUN(upsample_blk_launch(s3, U[U_UP3].up_W, 5, 4, n, 16, P, S4, cat, 8, 4, st));     // -> concat[32:48]
     if (lv.l[3]) {
         RUN(raw_to_wino_launch(c1, n, 20, 0, 20, S4, c1wd, 20, 0, st, 2));             // dilated pairs (w, w + 2)
         WCONV(U_CONV4_1, c1wd, S4, WG_OUT_WINO, d1w, 40);
@@ -1063,9 +1162,10 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
         CONV(U_CONV4_3, d2, S4, d1, 38, 0);
         CONV(U_SIDE4, d1, S4, s4, 2, 0);
     }
-    RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, st));     // -> concat[48:64]
+    if (lv.l[0]) RUN(upsample_wino_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, S4, catw, 8, 6, st));
+    else RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, st));     // -> concat[48:64]
     if (lv.l[0]) {
-        RUN(raw_to_wino_launch(cat, n, 8, 0, 8, S1, catw, 8, 0, st));
+        RUN(raw_to_wino_launch(cat, n, 8, 0, 2, S1, catw, 8, 0, st));                   // side_op1's 16 channels (the direct 1x1x1 unit wrote them raw)
         WCONV(U_MERGE1, catw, S1, WG_OUT_WINO, m1w, 14);
         WCONV(U_MERGE2, m1w, S1, WG_OUT_FINAL, nullptr, 0);                             // + merge_conv3 + sigmoid
     } else {

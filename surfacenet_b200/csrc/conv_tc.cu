@@ -597,6 +597,85 @@ upsample_wino_kernel(const __half* __restrict__ in, const float* __restrict__ W,
     }
 }
 
+// side_op1 (1x1x1, 32 -> 16, BatchNorm + sigmoid; nets/SurfaceNet.py:38) from a raw blk tensor straight into 16 channels of the
+// Winograd-domain concat tensor: one thread per output pair, fp32 FMAs on the CUDA cores (1,024 per pair: an HBM-bound pass --
+// 4 B read + 4 B written per voxel-channel), the consumer's input transform by shuffle as in upsample_wino_kernel.
+template <int CG_IN>
+__global__ void __launch_bounds__(256)
+side_wino_kernel(const __half* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ scale, const float* __restrict__ shift,
+                 int S, long long rows, __half* __restrict__ out, int cg_total, int cg_off) {
+    __shared__ float sW[CG_IN * 8 * 16];                                     // [c_in][16 outputs]
+    __shared__ float sS[32];
+    for (int i = threadIdx.x; i < CG_IN * 8 * 16; i += blockDim.x) sW[i] = Wt[i];
+    if (threadIdx.x < 16) { sS[threadIdx.x] = scale[threadIdx.x]; sS[16 + threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+    const int TP = S / 2;
+    const long long vol = (long long)S * S * S, volw = vol / 2;
+    const long long total = rows * TP;                                       // rows = n * S * S
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((total + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+        const bool active = i < total;
+        const long long ii = active ? i : total - 1;
+        const int tt = (int)(ii % TP);
+        const long long row = ii / TP;                                       // (n, d, h)
+        const long long n = row / ((long long)S * S), dh = row % ((long long)S * S);
+        float acc[2][16];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int o = 0; o < 16; ++o) acc[e][o] = 0.f;
+#pragma unroll
+        for (int g = 0; g < CG_IN; ++g) {
+            const __half* src = in + ((n * 2) * CG_IN + g) * vol * 8 + (dh * S + 2 * tt) * 8;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float v[8];
+                load_blk8(src + e * 8, (long long)CG_IN * vol * 8, 2, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4* w4 = reinterpret_cast<const float4*>(sW + (g * 8 + k) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w = w4[q];
+                        acc[e][4 * q + 0] = fmaf(v[k], w.x, acc[e][4 * q + 0]); acc[e][4 * q + 1] = fmaf(v[k], w.y, acc[e][4 * q + 1]);
+                        acc[e][4 * q + 2] = fmaf(v[k], w.z, acc[e][4 * q + 2]); acc[e][4 * q + 3] = fmaf(v[k], w.w, acc[e][4 * q + 3]);
+                    }
+                }
+            }
+        }
+        const bool first_t = tt == 0, last_t = tt == TP - 1;
+        const long long pos = dh * TP + tt;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float y[2][8];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) y[e][k] = 1.f / (1.f + expf(-fmaf(acc[e][8 * g + k], sS[8 * g + k], sS[16 + 8 * g + k])));
+            uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                float v[2][4];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float l = __shfl_up_sync(0xffffffffu, y[1][q + e], 1), r = __shfl_down_sync(0xffffffffu, y[0][q + e], 1);
+                    l = first_t ? 0.f : l; r = last_t ? 0.f : r;
+                    v[e][0] = l - y[1][q + e]; v[e][1] = y[0][q + e] + y[1][q + e]; v[e][2] = y[1][q + e] - y[0][q + e]; v[e][3] = y[0][q + e] - r;
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f) split_pack(v[0][f], v[1][f], hi[f][q >> 1], lo[f][q >> 1]);
+            }
+            if (active) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    __half* dst = out + (((n * 2) * 4 + f) * cg_total + cg_off + g) * volw * 8 + pos * 8;
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[f][0], hi[f][1], hi[f][2], hi[f][3]);
+                    *reinterpret_cast<uint4*>(dst + 4LL * cg_total * volw * 8) = make_uint4(lo[f][0], lo[f][1], lo[f][2], lo[f][3]);
+                }
+            }
+        }
+    }
+}
+
 static inline int ew_blocks(long long total) { return (int)std::min<long long>(cdiv(total, 256), 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -973,6 +1052,20 @@ static int upsample_wino_launch(const __half* in, const float* W, int k, int f, 
     return SN_OK;
 }
 
+// side_op1 -> Winograd-domain concat[0:16]; weights [C_in_pad][16] fp32 (TcUnit::side_w), BatchNorm scale / shift of the unit
+static int side_wino_launch(const Net& net, const __half* in, int n, int S, __half* out, int cg_total, int cg_off, cudaStream_t st) {
+    const TcState* ts = (const TcState*)net.tc;
+    const ConvUnit& su = net.units[U_SIDE1];
+    SN_CHECK_ARG(ts->units[U_SIDE1].side_w && su.Cin == 32 && su.Cout == 16 && (S == 16 || S == 32 || S == 64), "side_op1 (Winograd layout): unsupported shape");
+    const long long rows = (long long)n * S * S;
+    if (!rows) return SN_OK;
+    prof_begin(U_SIDE1, st);
+    side_wino_kernel<4><<<ew_blocks(rows * (S / 2)), 256, 0, st>>>(in, ts->units[U_SIDE1].side_w, su.scale, su.shift, S, rows, out, cg_total, cg_off);
+    prof_end(U_SIDE1, st);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+
 // halfs of workspace per pair-cube (per precision plane)
 static long long tc_halfs_per_pc(int D) {
     const long long V = (long long)D * D * D, V2 = V / 8, V4 = V / 64;
@@ -1124,7 +1217,8 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
     } else {
         CONV(U_CONV1_1, x0, S1, a1, 4, 0); CONV(U_CONV1_2, a1, S1, a2, 4, 0); CONV(U_CONV1_3, a2, S1, a1, 4, 0);
     }
-    CONV(U_SIDE1, a1, S1, cat, 8, 0);                                                  // side_op1 -> concat[0:16]
+    if (lv.l[0]) RUN(side_wino_launch(net, a1, n, S1, catw, 8, 0, st));                 // side_op1 -> Winograd-domain concat[0:16] (catw = the dead x0w|a1w|a2w region)
+    else CONV(U_SIDE1, a1, S1, cat, 8, 0);                                             // side_op1 -> concat[0:16]
     RUN(pool_launch(a1, n, 32, P, S1, p1, st));
     if (lv.l[1]) {
         RUN(raw_to_wino_launch(p1, n, 4, 0, 4, S2, p1w, 4, 0, st));
@@ -1165,7 +1259,6 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
     if (lv.l[0]) RUN(upsample_wino_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, S4, catw, 8, 6, st));
     else RUN(upsample_blk_launch(s4, U[U_UP4].up_W, 5, 4, n, 16, P, S4, cat, 8, 6, st));     // -> concat[48:64]
     if (lv.l[0]) {
-        RUN(raw_to_wino_launch(cat, n, 8, 0, 2, S1, catw, 8, 0, st));                   // side_op1's 16 channels (the direct 1x1x1 unit wrote them raw)
         WCONV(U_MERGE1, catw, S1, WG_OUT_WINO, m1w, 14);
         WCONV(U_MERGE2, m1w, S1, WG_OUT_FINAL, nullptr, 0);                             // + merge_conv3 + sigmoid
     } else {

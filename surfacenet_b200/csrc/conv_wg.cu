@@ -46,6 +46,7 @@ struct ConvWgParams {
     int S, n_pc, dil, n_cblk, cg_in;
     int TP, tp_shift, TH, HH, HD;   // pairs per row (= S/2), log2(TP), rows per tile (128 / TP), halo extents in h / d
     int NA, NB;                     // A ring stages, weight ring slots (3 taps per slot)
+    int hs, d_step;                 // hs: S = 8 geometry (below); d_step: d-planes per tile (AD, or 4 in the hs geometry)
     int a_prec_bytes;               // bytes of one precision plane of one A stage = 2 groups * HD*HH*TP*16
     long long n_tiles;              // tiles_h * tiles_d * n_pc * n_ntiles; every tile = 4 frequency passes
     int tiles_h, tiles_d, n_ntiles;
@@ -65,7 +66,7 @@ struct WgTile { int nt, pc, d0, h0; };
 __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int AD) {
     WgTile c;
     uint32_t q = t / (uint32_t)p.tiles_h; c.h0 = (int)(t - q * p.tiles_h) * p.TH; t = q;
-    q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * AD; t = q;
+    q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * p.d_step; t = q;
     q = t / (uint32_t)p.n_pc; c.pc = (int)(t - q * p.n_pc);
     c.nt = (int)q;
     return c;
@@ -135,19 +136,24 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         int s = 0; uint32_t ph = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const WgTile c = wg_tile(p, t, AD);
+            // hs geometry (S = 8: a row holds only 4 pairs, 128 rows = 4 d-planes x 8 h-rows): the tile carries NO h halo -- a halo would break
+            // the linear row pitch across planes -- and is loaded once per kh tap, shifted by (kh - 1) * dil rows (out-of-bounds rows are zeros)
+            const int n_sh = p.hs ? 3 : 1;
             for (int f = 0; f < 4; ++f)
-                for (int cb = 0; cb < p.n_cblk; ++cb) {
-                    mbar_wait(&a_empty[s], ph ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(&a_full[s], a_stage_bytes);
+                for (int cb = 0; cb < p.n_cblk; ++cb)
+                    for (int kh = 0; kh < n_sh; ++kh) {
+                        mbar_wait(&a_empty[s], ph ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(&a_full[s], a_stage_bytes);
+                            const int h_lo = p.hs ? (kh - 1) * pad : c.h0 - pad;
 #pragma unroll
-                        for (int pr = 0; pr < 2; ++pr)
-                            tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
-                                        0, c.h0 - pad, c.d0 - pad, ((c.pc * 2 + pr) * 4 + f) * p.cg_in + 2 * cb);
+                            for (int pr = 0; pr < 2; ++pr)
+                                tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
+                                            0, h_lo, c.d0 - pad, ((c.pc * 2 + pr) * 4 + f) * p.cg_in + 2 * cb);
+                        }
+                        __syncwarp();
+                        if (++s == NA) { s = 0; ph ^= 1; }
                     }
-                    __syncwarp();
-                    if (++s == NA) { s = 0; ph ^= 1; }
-                }
         }
     } else if (warp == 17) {
         // ===== B producer: the (frequency, channel block, tap) weight stages, TPS per ring slot =====
@@ -162,7 +168,15 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                     mbar_wait(&b_empty[s], ph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&b_full[s], slot_bytes);
-                        bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * slot_bytes, slot_bytes, &b_full[s]);
+                        if (!p.hs) {
+                            bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * slot_bytes, slot_bytes, &b_full[s]);
+                        } else {                                            // slot = the three kd taps of (block it / 3, kh = it % 3): stages kd*3 + kh
+                            const uint32_t stage_bytes = slot_bytes / TPS;
+                            const int cb = it / 3, kh = it - 3 * cb;
+                            for (int kd = 0; kd < 3; ++kd)
+                                bulk_load(smB + (size_t)s * b_slot_bytes + (size_t)kd * stage_bytes, wsrc + (size_t)(cb * 9 + kd * 3 + kh) * stage_bytes,
+                                          stage_bytes, &b_full[s]);
+                        }
                     }
                     __syncwarp();
                     if (++s == NB) { s = 0; ph ^= 1; }
@@ -205,13 +219,18 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 tc_fence_after();
                 uint32_t acc_flag = me ? 1u : 0u;
                 for (int cb = 0; cb < p.n_cblk; ++cb) {
-                    mbar_wait(&a_full[sa], pha);
+                    if (!p.hs) mbar_wait(&a_full[sa], pha);
                     tc_fence_after();
-                    const uint32_t a_base16 = smA16 + sa * a_stage16;
+                    uint32_t a_base16 = smA16 + sa * a_stage16;
                     const bool paired = p.pair_last && cb == p.n_cblk - 1;
                     const int n_slots = paired ? 2 : 3;
                     uint32_t a_kd = a_base16 | a_lbo;
                     for (int sl = 0; sl < n_slots; ++sl, a_kd += kd_step, ++g) {
+                        if (p.hs) {                                          // one h-shifted A stage per slot (slot = kh, its taps = kd 0..2)
+                            mbar_wait(&a_full[sa], pha);
+                            a_base16 = smA16 + sa * a_stage16;
+                            a_kd = a_base16 | a_lbo;
+                        }
                         mbar_wait(&b_full[sb], phb);
                         mbar_wait(&tok[me], (g & 1) ^ (me ? 0u : 1u));  // my turn: hi issuer after lo(g-1), lo issuer after hi(g)
                         tc_fence_after();
@@ -219,7 +238,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                             const uint32_t b_lo32 = (smB16 + sb * b_slot16) | b_lbo;
 #pragma unroll
                             for (int kk = 0; kk < TPS; ++kk) {
-                                const uint32_t a_tap = paired ? a_base16 + pair_tbl[sl * TPS + kk] : a_kd + kk * kh_step;
+                                const uint32_t a_tap = paired ? a_base16 + pair_tbl[sl * TPS + kk] : a_kd + kk * (p.hs ? kd_step : kh_step);
                                 const uint64_t db = ((uint64_t)ab_hi32 << 32) | (b_lo32 + kk * tapB16);
 #pragma unroll
                                 for (int a = 0; a < AD; ++a) {
@@ -234,7 +253,13 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                         __syncwarp();
                         acc_flag = 1u;
                         if (++sb == NB) { sb = 0; phb ^= 1; }
+                        if (p.hs) {
+                            if (elect_one()) tc_commit(&a_empty[sa]);
+                            __syncwarp();
+                            if (++sa == NA) { sa = 0; pha ^= 1; }
+                        }
                     }
+                    if (p.hs) continue;
                     if (elect_one()) tc_commit(&a_empty[sa]);
                     __syncwarp();
                     if (++sa == NA) { sa = 0; pha ^= 1; }
@@ -249,7 +274,8 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WG_EPI_REGS));
         const int q = warp & 3, cq = warp >> 2;
         const int m = q * 32 + lane;
-        const int hl = m >> p.tp_shift, tt = m & (p.TP - 1);
+        const int hrow = m >> p.tp_shift, tt = m & (p.TP - 1);
+        const int hl = p.hs ? (hrow & 7) : hrow, dl = p.hs ? (hrow >> 3) : 0;   // hs geometry: 128 rows = 4 planes x 8 rows x 4 pairs
         const int S = p.S, TP = p.TP;
         const long long vol = (long long)S * S * S;
         const int act = p.act, dil = p.dil;
@@ -323,7 +349,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { y0[i] = P0[kk * 8 + i]; y1[i] = P1[kk * 8 + i]; }
                     }
-                const int d = c.d0 + a;
+                const int d = c.d0 + a + dl;
                 const bool ok = live && (d < S) && (h < S);
                 const int ch0 = c_base + jc;
                 if (live) {
@@ -578,17 +604,18 @@ void wg_destroy(Net& net) {
     for (int u = 0; u < kNumUnits; ++u) { cudaFree(st->wg[u].w); cudaFree(st->wg[u].scale); cudaFree(st->wg[u].shift); st->wg[u] = WgUnit(); }
 }
 
-// supported geometry: a tile is 128 pairs = (128 / TP) full rows of TP = S/2 pairs, TP in {8, 16, 32}
+// supported geometry: a tile is 128 pairs = (128 / TP) full rows of TP = S/2 pairs, TP in {8, 16, 32}; S = 8 (TP = 4): 4 d-planes x 8 rows,
+// no tap pairing, N tiles of 80 / 112 (the units that meet S = 8: conv2_x at D = 16, conv3_x / conv4_x at D = 32)
 bool wg_supported(const Net& net, int u, int S) {
     const TcState* st = (const TcState*)net.tc;
-    return st && st->wg[u].on && wg_unit_enabled(u) && (S == 16 || S == 32 || S == 64);
+    return st && st->wg[u].on && wg_unit_enabled(u) && (S == 16 || S == 32 || S == 64 || (S == 8 && !st->wg[u].pair_last && st->wg[u].nt_size[0] != 32));
 }
 
 struct WgCfg { int AD, NA, NB; size_t smem; };
 
 static size_t wg_smem_bytes(int S, int N, int dil, int AD, int NA, int NB) {
     const int TP = S / 2, TH = 128 / TP;
-    const size_t a_stage = (size_t)2 * 2 * (AD + 2 * dil) * (TH + 2 * dil) * TP * 16;
+    const size_t a_stage = (S == 8) ? (size_t)2 * 2 * (4 + 2 * dil) * 8 * TP * 16 : (size_t)2 * 2 * (AD + 2 * dil) * (TH + 2 * dil) * TP * 16;
     return (size_t)NA * a_stage + (size_t)NB * N * 64 * 3 + (2 * WG_MAX_NA + 2 * WG_MAX_NB + 6) * 8 + 16 + 64 + 3 * 128 * 2 * 4 +
            (2 * WG_MAX_C + 128) * 4 + 64;
 }
@@ -602,7 +629,7 @@ static WgCfg wg_config(int S, int N, int dil) {
     if (env_ad && N == 32 && (env_ad == 2 || env_ad == 4)) c.AD = env_ad;
     c.AD = std::min(c.AD, S);
     const size_t budget = 220 * 1024;
-    c.NA = env_na ? std::max(2, std::min(WG_MAX_NA, env_na)) : 3;
+    c.NA = env_na ? std::max(2, std::min(WG_MAX_NA, env_na)) : (S == 8 ? 4 : 3);
     while (c.NA > 2 && wg_smem_bytes(S, N, dil, c.AD, c.NA, 2) > budget) --c.NA;
     c.NB = 2;
     while (c.NB < WG_MAX_NB && wg_smem_bytes(S, N, dil, c.AD, c.NA, c.NB + 1) <= budget) ++c.NB;
@@ -636,11 +663,12 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     const WgCfg cfg = wg_config(S, N, cu.dil);
     ConvWgParams p{};
     p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.n_cblk = wu.n_cblk; p.cg_in = cg_in_total ? cg_in_total : wu.Cin_pad / 8;
-    p.TP = S / 2; p.tp_shift = (p.TP == 8) ? 3 : (p.TP == 16 ? 4 : 5); p.TH = 128 / p.TP;
-    p.HH = p.TH + 2 * cu.dil; p.HD = cfg.AD + 2 * cu.dil;
+    p.hs = (S == 8) ? 1 : 0;
+    p.TP = S / 2; p.tp_shift = (p.TP == 4) ? 2 : (p.TP == 8) ? 3 : (p.TP == 16 ? 4 : 5); p.TH = p.hs ? 8 : 128 / p.TP;
+    p.HH = p.hs ? 8 : p.TH + 2 * cu.dil; p.HD = (p.hs ? 4 : cfg.AD) + 2 * cu.dil; p.d_step = p.hs ? 4 : cfg.AD;
     p.NA = cfg.NA; p.NB = cfg.NB;
     p.a_prec_bytes = 2 * p.HD * p.HH * p.TP * 16;
-    p.tiles_h = S / p.TH; p.tiles_d = (int)cdiv(S, cfg.AD); p.n_ntiles = wu.n_ntiles;
+    p.tiles_h = S / p.TH; p.tiles_d = (int)cdiv(S, p.d_step); p.n_ntiles = wu.n_ntiles;
     p.n_tiles = (long long)n_pc * p.tiles_d * p.tiles_h * wu.n_ntiles;
     for (int t = 0; t < TC_MAX_NT; ++t) { p.nt_off[t] = wu.nt_off[t]; p.nt_nc[t] = wu.nt_nc[t]; p.nt_woff[t] = wu.nt_woff[t]; }
     p.pair_last = wu.pair_last; p.stages_per_f = wu.stages_per_f;

@@ -47,6 +47,7 @@ struct ConvWgParams {
     int TP, tp_shift, TH, HH, HD;   // pairs per row (= S/2), log2(TP), rows per tile (128 / TP), halo extents in h / d
     int NA, NB;                     // A ring stages, weight ring slots (3 taps per slot)
     int hs, d_step;                 // hs: S = 8 geometry (below); d_step: d-planes per tile (AD, or 4 in the hs geometry)
+    int dbg;                        // SN_WG_DEBUG (timing experiments only): 1 = no output stores, 2 = no output math after the drains
     int a_prec_bytes;               // bytes of one precision plane of one A stage = 2 groups * HD*HH*TP*16
     long long n_tiles;              // tiles_h * tiles_d * n_pc * n_ntiles; every tile = 4 frequency passes
     int tiles_h, tiles_d, n_ntiles;
@@ -329,10 +330,43 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 }
                 tc_fence_before();                                         // TMEM reads done -> the MMA warps may overwrite this set
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+                // Work that does not need the last pass is done HERE, while the MMA warps are busy with the next pass: the MMA may run only two
+                // passes ahead of the drains, so everything left for after pass 3 is on its critical path (merge_conv: 15 % of the issuers'
+                // time was spent waiting for this).  After pass 2, y[2t] = M0 + M1 + M2 is final -> BatchNorm + activation in place, and the
+                // Winograd-domain output's frequency 3, V3 = y[2t] - y[2t+2], needs nothing else.  After pass 3: BatchNorm + activation of y[2t+1].
+                if (f >= 2) {
+#pragma unroll
+                    for (int ck = 0; ck < NCH; ++ck) {
+                        const int a = ck / NQ, k = ck - a * NQ;
+                        if (col0 + k * 8 < N) {
+                            float* yy = (f == 2) ? &P0[ck * 8] : &P1[ck * 8];
+                            const int ch0 = c_base + k * 8;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) yy[i] = tc_act(fmaf(yy[i], sc_s[ch0 + i], sh_s[ch0 + i]), act);
+                            if (OUT == WG_OUT_WINO && f == 2) {
+                                uint32_t hi[4], lo[4];
+#pragma unroll
+                                for (int i = 0; i < 8; i += 2) {
+                                    float r0 = __shfl_down_sync(0xffffffffu, yy[i], dil), r1 = __shfl_down_sync(0xffffffffu, yy[i + 1], dil);
+                                    r0 = last_t ? 0.f : r0; r1 = last_t ? 0.f : r1;
+                                    split_pack(yy[i] - r0, yy[i + 1] - r1, hi[i >> 1], lo[i >> 1]);
+                                }
+                                const int d = c.d0 + a + dl;
+                                if (d < S && h < S && !(p.dbg & 1)) {
+                                    const uint32_t o = (uint32_t)c.pc * 2u * prec_stride4 + (uint32_t)(p.cg_out_off + (ch0 >> 3)) * cg_stride4 +
+                                                       (uint32_t)((d * S + h) * TP + tt) + 3u * f_stride4;
+                                    out4[o] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                    out4[o + prec_stride4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                                }
+                            }
+                        }
+                    }
+                }
             }
-            // ---- all four frequencies are in: BatchNorm + activation, then the output format of this unit.  ONE copy of the chunk code in a
-            //      rolled loop (unrolling it over the chunks was measured slower: instruction-cache misses); the chunk's 16 registers are
-            //      picked out of the accumulator arrays by predicated moves ----
+            // ---- all four frequencies are in (BatchNorm + activation already applied): the output format of this unit.  ONE copy of the chunk
+            //      code in a rolled loop (unrolling it over the chunks was measured slower: instruction-cache misses); the chunk's 16 registers
+            //      are picked out of the accumulator arrays by predicated moves ----
+            if (p.dbg & 2) continue;
             float z0 = 0.f, z1 = 0.f;
             const uint32_t pc_base4 = (uint32_t)c.pc * 2u * prec_stride4 + (uint32_t)(p.cg_out_off + (c_base >> 3)) * cg_stride4;
 #pragma unroll 1
@@ -350,16 +384,8 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                         for (int i = 0; i < 8; ++i) { y0[i] = P0[kk * 8 + i]; y1[i] = P1[kk * 8 + i]; }
                     }
                 const int d = c.d0 + a + dl;
-                const bool ok = live && (d < S) && (h < S);
+                const bool ok = live && (d < S) && (h < S) && !(p.dbg & 1);
                 const int ch0 = c_base + jc;
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float sc = sc_s[ch0 + i], sh = sh_s[ch0 + i];
-                        y0[i] = tc_act(fmaf(y0[i], sc, sh), act);
-                        y1[i] = tc_act(fmaf(y1[i], sc, sh), act);
-                    }
-                }
                 if (OUT == WG_OUT_FINAL) {
                     if (live) {
 #pragma unroll
@@ -368,24 +394,24 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 } else if (OUT == WG_OUT_WINO) {
                     // the next unit's input transform: d0 = left neighbour's second voxel, d1, d2 = this pair, d3 = right neighbour's first voxel
                     // (neighbour pair of the same row / sub-lattice = lane -+ dil; zero outside the row)
-                    if (live) {
-                        uint32_t hi[4][4], lo[4][4];
+                    if (live) {                                              // frequencies 0..2 (3 was written after pass 2)
+                        uint32_t hi[3][4], lo[3][4];
 #pragma unroll
                         for (int i = 0; i < 8; i += 2) {
-                            float v[2][4];
+                            float v[2][3];
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                float l = __shfl_up_sync(0xffffffffu, y1[i + e], dil), r = __shfl_down_sync(0xffffffffu, y0[i + e], dil);
-                                l = first_t ? 0.f : l; r = last_t ? 0.f : r;
-                                v[e][0] = l - y1[i + e]; v[e][1] = y0[i + e] + y1[i + e]; v[e][2] = y1[i + e] - y0[i + e]; v[e][3] = y0[i + e] - r;
+                                float l = __shfl_up_sync(0xffffffffu, y1[i + e], dil);
+                                l = first_t ? 0.f : l;
+                                v[e][0] = l - y1[i + e]; v[e][1] = y0[i + e] + y1[i + e]; v[e][2] = y1[i + e] - y0[i + e];
                             }
 #pragma unroll
-                            for (int f = 0; f < 4; ++f) split_pack(v[0][f], v[1][f], hi[f][i >> 1], lo[f][i >> 1]);
+                            for (int f = 0; f < 3; ++f) split_pack(v[0][f], v[1][f], hi[f][i >> 1], lo[f][i >> 1]);
                         }
                         if (ok) {
                             const uint32_t o = pc_base4 + (uint32_t)k * cg_stride4 + (uint32_t)((d * S + h) * TP + tt);
 #pragma unroll
-                            for (int f = 0; f < 4; ++f) {
+                            for (int f = 0; f < 3; ++f) {
                                 out4[o + f * f_stride4] = make_uint4(hi[f][0], hi[f][1], hi[f][2], hi[f][3]);
                                 out4[o + f * f_stride4 + prec_stride4] = make_uint4(lo[f][0], lo[f][1], lo[f][2], lo[f][3]);
                             }
@@ -663,6 +689,8 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     const WgCfg cfg = wg_config(S, N, cu.dil);
     ConvWgParams p{};
     p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.n_cblk = wu.n_cblk; p.cg_in = cg_in_total ? cg_in_total : wu.Cin_pad / 8;
+    static const int env_dbg = getenv("SN_WG_DEBUG") ? atoi(getenv("SN_WG_DEBUG")) : 0;
+    p.dbg = env_dbg;
     p.hs = (S == 8) ? 1 : 0;
     p.TP = S / 2; p.tp_shift = (p.TP == 4) ? 2 : (p.TP == 8) ? 3 : (p.TP == 16 ? 4 : 5); p.TH = p.hs ? 8 : 128 / p.TP;
     p.HH = p.hs ? 8 : p.TH + 2 * cu.dil; p.HD = (p.hs ? 4 : cfg.AD) + 2 * cu.dil; p.d_step = p.hs ? 4 : cfg.AD;

@@ -80,7 +80,7 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 // Warps: 0..15 epilogue, 16 A producer, 17 B producer, 18 issues the A_hi MMAs, 19 the A_lo MMAs (+ TMEM allocation).  One warp's instruction
 // stream (~15 dependent instructions per MMA: descriptor words through R2UR) cannot feed the tensor pipe at 160 cycles per tap with a
 // single CTA per SM, hence two issuers.  Both add into the corr columns, and fp32 accumulation with truncation is not associative, so the
-// two warps hand a token back and forth (tok[0]: the hi issuer may issue slot g, tok[1]: the lo issuer may issue slot g): the MMAs enter the tensor
+// two warps hand a token back and forth (tok[1]: the hi issuer may issue slot g, tok[0]: the lo issuer may issue slot g): the MMAs enter the tensor
 // pipe in ONE fixed order (hi slot 0, lo slot 0, hi slot 1, ...) -> bit-reproducible results, and the pass-opening A_hi MMA
 // (accumulate = 0, it initialises the corr columns) is always ahead of the first A_lo MMA.  Each warp prepares its descriptors
 // while the other one issues; only the three UTCHMMA + the hand-off are serialised.
@@ -100,7 +100,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)NB * b_slot_bytes);
     uint64_t* a_full = bars, *a_empty = bars + WG_MAX_NA, *b_full = bars + 2 * WG_MAX_NA, *b_empty = b_full + WG_MAX_NB;
     uint64_t* acc_full = b_empty + WG_MAX_NB, *acc_empty = acc_full + 2, *tok = acc_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tok + 2 + 6);     // its own 64-byte line, away from the barriers (tcgen05.alloc writes it)
     uint32_t* pair_tbl = tmem_slot + 4 + ((warp == 19) ? 8 : 0);         // [2][8] tap-pair descriptors, private per MMA warp
     float* zbuf = reinterpret_cast<float*>(tmem_slot + 4 + 16);         // [3][128][2] partial merge_conv3 sums of the column quarters 1..3
     float* sc_s = zbuf + 768;                                           // [WG_MAX_C] folded BatchNorm scale / shift, [128] merge_conv3 weights
@@ -117,6 +117,8 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 512); }
         mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);            // the issue-order tokens
+        // the hi issuer owns the token at the start: phase 0 of its barrier is completed here
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&in_map) : "memory");
     }
@@ -233,7 +235,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                             a_kd = a_base16 | a_lbo;
                         }
                         mbar_wait(&b_full[sb], phb);
-                        mbar_wait(&tok[me], (g & 1) ^ (me ? 0u : 1u));  // my turn: hi issuer after lo(g-1), lo issuer after hi(g)
+                        mbar_wait(&tok[me ^ 1], g & 1);                        // my turn: hi issuer after lo(g-1) (phase 0: the initial token), lo issuer after hi(g)
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t b_lo32 = (smB16 + sb * b_slot16) | b_lbo;
@@ -248,7 +250,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                                 }
                                 acc_flag = 1u;
                             }
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[me ^ 1])) : "memory");   // pass the token
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[me])) : "memory");   // pass the token
                             tc_commit(&b_empty[sb]);
                         }
                         __syncwarp();
@@ -642,7 +644,7 @@ struct WgCfg { int AD, NA, NB; size_t smem; };
 static size_t wg_smem_bytes(int S, int N, int dil, int AD, int NA, int NB) {
     const int TP = S / 2, TH = 128 / TP;
     const size_t a_stage = (S == 8) ? (size_t)2 * 2 * (4 + 2 * dil) * 8 * TP * 16 : (size_t)2 * 2 * (AD + 2 * dil) * (TH + 2 * dil) * TP * 16;
-    return (size_t)NA * a_stage + (size_t)NB * N * 64 * 3 + (2 * WG_MAX_NA + 2 * WG_MAX_NB + 6) * 8 + 16 + 64 + 3 * 128 * 2 * 4 +
+    return (size_t)NA * a_stage + (size_t)NB * N * 64 * 3 + (2 * WG_MAX_NA + 2 * WG_MAX_NB + 6 + 6) * 8 + 16 + 64 + 3 * 128 * 2 * 4 +
            (2 * WG_MAX_C + 128) * 4 + 64;
 }
 

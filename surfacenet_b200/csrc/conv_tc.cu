@@ -977,6 +977,12 @@ static int conv_tc_launch(const Net& net, int u, const __half* in, int n_pc, int
     } else {
         std::vector<TileCfg> cand = tile_candidates(cu, Nmax, S, P);
         cfg = cand.back();
+        // 1x1x1 units (the side outputs: HBM-bound passes) get a fixed configuration -- with the 3x3x3 units on the Winograd kernel they are the
+        // only direct launches of a supported cube size, so no first-call measurement sweep is left in the default path
+        if (cu.K == 1) {
+            cfg = TileCfg{1, 3, 1, 0};
+            for (const TileCfg& c : cand) if (c.persist == 1 && c.NB == 3 && c.tps == 0 && c.AD > cfg.AD) cfg = c;
+        } else
         if (env_tune && cand.size() > 1 && work >= (1 << 15)) {
             cudaEvent_t e0, e1;
             SN_CUDA(cudaEventCreate(&e0)); SN_CUDA(cudaEventCreate(&e1));

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsurfacenet_b200.so")
+LIB_PATH = os.environ.get("SN_LIB_PATH") or os.path.join(_HERE, "libsurfacenet_b200.so")     # SN_LIB_PATH: A/B runs of two builds (tools/)
 
 SN_OK, SN_ERR_INVALID, SN_ERR_CUDA, SN_ERR_DOMAIN, SN_ERR_NOMEM = 0, -1, -2, -3, -4
 MODE_FP32, MODE_TC_EXACT, MODE_TC_FAST = 0, 1, 2

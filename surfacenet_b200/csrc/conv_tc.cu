@@ -1214,13 +1214,13 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
 #define RUN(x) do { rc = (x); if (rc != SN_OK) return rc; } while (0)
 #define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))
 #define WCONV(u, in, S, fmt, out, cgt) do { prof_begin(u, st); rc = wg_conv_launch(net, u, in, n, S, fmt, out, cgt, 0, prob_out, st); prof_end(u, st); if (rc != SN_OK) return rc; } while (0)
-    RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
-    if (lv.l[0]) {
-        RUN(raw_to_wino_launch(x0, n, 2, 0, 2, S1, x0w, 2, 0, st));
+    if (lv.l[0] && ((TcState*)net.tc)->wg[U_CONV1_1].pair_last) {
+        RUN(pack_wino_launch(X, n, 6, S1, x0w, st));                                    // X fp32 -> conv1_1's Winograd-domain operand in one pass
         WCONV(U_CONV1_1, x0w, S1, WG_OUT_WINO, a1w, 4);
         WCONV(U_CONV1_2, a1w, S1, WG_OUT_WINO, a2w, 4);
         WCONV(U_CONV1_3, a2w, S1, WG_OUT_RAW, a1, 4);
     } else {
+        RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
         CONV(U_CONV1_1, x0, S1, a1, 4, 0); CONV(U_CONV1_2, a1, S1, a2, 4, 0); CONV(U_CONV1_3, a2, S1, a1, 4, 0);
     }
     if (lv.l[0]) RUN(side_wino_launch(net, a1, n, S1, catw, 8, 0, st));                 // side_op1 -> Winograd-domain concat[0:16] (catw = the dead x0w|a1w|a2w region)

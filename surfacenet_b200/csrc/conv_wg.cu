@@ -74,6 +74,7 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 }
 
 // AD = d-planes per CTA, N = output channels of the N tile (padded to 16),
+// HS = the S = 8 geometry (compile time: its branches sit in the MMA issue loop, where every instruction counts),
 // OUT = output format of the unit (WG_OUT_*): a template parameter so that only ONE epilogue variant is in the instruction stream
 // (the first version carried all three, fully unrolled over the column chunks: 150 KB of straight-line code per tile, 23 % of the
 // stall samples were instruction-cache misses and the WINO units ran at half the speed of the RAW ones).
@@ -84,7 +85,7 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 // pipe in ONE fixed order (hi slot 0, lo slot 0, hi slot 1, ...) -> bit-reproducible results, and the pass-opening A_hi MMA
 // (accumulate = 0, it initialises the corr columns) is always ahead of the first A_lo MMA.  Each warp prepares its descriptors
 // while the other one issues; only the three UTCHMMA + the hand-off are serialised.
-template <int AD, int N, int OUT>
+template <int AD, int N, int OUT, bool HS>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p) {
     constexpr int TPS = 3;                                             // taps per weight slot: the three kh taps of one kd
@@ -141,14 +142,14 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
             const WgTile c = wg_tile(p, t, AD);
             // hs geometry (S = 8: a row holds only 4 pairs, 128 rows = 4 d-planes x 8 h-rows): the tile carries NO h halo -- a halo would break
             // the linear row pitch across planes -- and is loaded once per kh tap, shifted by (kh - 1) * dil rows (out-of-bounds rows are zeros)
-            const int n_sh = p.hs ? 3 : 1;
+            const int n_sh = HS ? 3 : 1;
             for (int f = 0; f < 4; ++f)
                 for (int cb = 0; cb < p.n_cblk; ++cb)
                     for (int kh = 0; kh < n_sh; ++kh) {
                         mbar_wait(&a_empty[s], ph ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(&a_full[s], a_stage_bytes);
-                            const int h_lo = p.hs ? (kh - 1) * pad : c.h0 - pad;
+                            const int h_lo = HS ? (kh - 1) * pad : c.h0 - pad;
 #pragma unroll
                             for (int pr = 0; pr < 2; ++pr)
                                 tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
@@ -171,7 +172,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                     mbar_wait(&b_empty[s], ph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&b_full[s], slot_bytes);
-                        if (!p.hs) {
+                        if (!HS) {
                             bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * slot_bytes, slot_bytes, &b_full[s]);
                         } else {                                            // slot = the three kd taps of (block it / 3, kh = it % 3): stages kd*3 + kh
                             const uint32_t stage_bytes = slot_bytes / TPS;
@@ -222,14 +223,14 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 tc_fence_after();
                 uint32_t acc_flag = me ? 1u : 0u;
                 for (int cb = 0; cb < p.n_cblk; ++cb) {
-                    if (!p.hs) mbar_wait(&a_full[sa], pha);
+                    if (!HS) mbar_wait(&a_full[sa], pha);
                     tc_fence_after();
                     uint32_t a_base16 = smA16 + sa * a_stage16;
                     const bool paired = p.pair_last && cb == p.n_cblk - 1;
                     const int n_slots = paired ? 2 : 3;
                     uint32_t a_kd = a_base16 | a_lbo;
                     for (int sl = 0; sl < n_slots; ++sl, a_kd += kd_step, ++g) {
-                        if (p.hs) {                                          // one h-shifted A stage per slot (slot = kh, its taps = kd 0..2)
+                        if (HS) {                                          // one h-shifted A stage per slot (slot = kh, its taps = kd 0..2)
                             mbar_wait(&a_full[sa], pha);
                             a_base16 = smA16 + sa * a_stage16;
                             a_kd = a_base16 | a_lbo;
@@ -241,7 +242,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                             const uint32_t b_lo32 = (smB16 + sb * b_slot16) | b_lbo;
 #pragma unroll
                             for (int kk = 0; kk < TPS; ++kk) {
-                                const uint32_t a_tap = paired ? a_base16 + pair_tbl[sl * TPS + kk] : a_kd + kk * (p.hs ? kd_step : kh_step);
+                                const uint32_t a_tap = paired ? a_base16 + pair_tbl[sl * TPS + kk] : a_kd + kk * (HS ? kd_step : kh_step);
                                 const uint64_t db = ((uint64_t)ab_hi32 << 32) | (b_lo32 + kk * tapB16);
 #pragma unroll
                                 for (int a = 0; a < AD; ++a) {
@@ -256,13 +257,13 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                         __syncwarp();
                         acc_flag = 1u;
                         if (++sb == NB) { sb = 0; phb ^= 1; }
-                        if (p.hs) {
+                        if (HS) {
                             if (elect_one()) tc_commit(&a_empty[sa]);
                             __syncwarp();
                             if (++sa == NA) { sa = 0; pha ^= 1; }
                         }
                     }
-                    if (p.hs) continue;
+                    if (HS) continue;
                     if (elect_one()) tc_commit(&a_empty[sa]);
                     __syncwarp();
                     if (++sa == NA) { sa = 0; pha ^= 1; }
@@ -278,7 +279,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         const int q = warp & 3, cq = warp >> 2;
         const int m = q * 32 + lane;
         const int hrow = m >> p.tp_shift, tt = m & (p.TP - 1);
-        const int hl = p.hs ? (hrow & 7) : hrow, dl = p.hs ? (hrow >> 3) : 0;   // hs geometry: 128 rows = 4 planes x 8 rows x 4 pairs
+        const int hl = HS ? (hrow & 7) : hrow, dl = HS ? (hrow >> 3) : 0;   // hs geometry: 128 rows = 4 planes x 8 rows x 4 pairs
         const int S = p.S, TP = p.TP;
         const long long vol = (long long)S * S * S;
         const int act = p.act, dil = p.dil;
@@ -476,8 +477,8 @@ raw_to_wino_kernel(const __half* __restrict__ in, int cg_in_total, int cg_in_off
         const __half* src = in + ((n * 2) * cg_in_total + cg_in_off + g) * vol * 8 + (dh * S) * 8;
         const long long prec_in = (long long)cg_in_total * vol * 8;
         float d[4][8];
-#pragma unroll
         const int wa = (dil == 1) ? 2 * t : (t & 1) + 4 * (t >> 1);            // dil = 2: pair t = 2j + parity -> voxels parity + 4j, + 2
+#pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int w = wa + (k - 1) * dil;                                   // d0..d3 = x[wa - dil], x[wa], x[wa + dil], x[wa + 2 dil]
             if (w >= 0 && w < S) {
@@ -514,6 +515,54 @@ raw_to_wino_kernel(const __half* __restrict__ in, int cg_in_total, int cg_in_off
             *reinterpret_cast<uint4*>(dst + 4LL * cg_out_total * volw * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
+}
+
+// fp32 NCDHW network input X (n, C <= 8, S^3) (the mean-subtracted CVC, utils/CVC.py:104-111) -> channel group 0 of a wino blk tensor with 2 groups
+// (conv1_1 reads 16 padded channels; its 6 real ones sit in group 0 and the unit pairs TAPS as K halves, so group 1 is never multiplied and
+// is left unwritten).  One thread per output pair; the two neighbour voxels come from the adjacent lanes.  Replaces pack_blk + raw_to_wino.
+__global__ void __launch_bounds__(256)
+pack_wino_kernel(const float* __restrict__ x, int C, int S, long long total, __half* __restrict__ out) {
+    const int TP = S / 2;
+    const long long vol = (long long)S * S * S, volw = vol / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((total + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+        const bool active = i < total;
+        const long long ii = active ? i : total - 1;
+        const int t = (int)(ii % TP);
+        const long long row = ii / TP;                                       // (n, d, h)
+        const long long n = row / ((long long)S * S), dh = row % ((long long)S * S);
+        const bool first_t = t == 0, last_t = t == TP - 1;
+        float v[4][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float2 y = make_float2(0.f, 0.f);
+            if (c < C) y = __ldg(reinterpret_cast<const float2*>(x + (n * C + c) * vol + dh * S + 2 * t));
+            float l = __shfl_up_sync(0xffffffffu, y.y, 1), r = __shfl_down_sync(0xffffffffu, y.x, 1);
+            l = first_t ? 0.f : l; r = last_t ? 0.f : r;
+            v[0][c] = l - y.y; v[1][c] = y.x + y.y; v[2][c] = y.y - y.x; v[3][c] = y.x - r;
+        }
+        if (active) {
+            const long long pos = dh * TP + t;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_pack(v[f][2 * e], v[f][2 * e + 1], hi[e], lo[e]);
+                __half* dst = out + (((n * 2) * 4 + f) * 2 + 0) * volw * 8 + pos * 8;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + 4LL * 2 * volw * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+}
+
+int pack_wino_launch(const float* x, int n, int C, int S, __half* out_wino, cudaStream_t stream) {
+    const long long total = (long long)n * S * S * (S / 2);
+    if (!total) return SN_OK;
+    SN_CHECK_ARG(C <= 8 && (S == 16 || S == 32 || S == 64), "pack_wino: unsupported shape (C=%d, S=%d)", C, S);
+    const int blocks = (int)std::min<long long>(cdiv(total, 256), 148 * 16);
+    pack_wino_kernel<<<blocks, 256, 0, stream>>>(x, C, S, total, out_wino);
+    SN_LAUNCHED();
+    return SN_OK;
 }
 
 int raw_to_wino_launch(const __half* in_raw, int n, int cg_in_total, int cg_in_off, int cg_count, int S, __half* out_wino, int cg_out_total,
@@ -666,14 +715,14 @@ static WgCfg wg_config(int S, int N, int dil) {
     return c;
 }
 
-template <int AD, int N, int OUT>
+template <int AD, int N, int OUT, bool HS>
 static int wg_launch_t(const CUtensorMap& map, const ConvWgParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, N, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, N, OUT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
         attr_set = true;
     }
-    conv_wg_kernel<AD, N, OUT><<<grid, WG_THREADS, smem, stream>>>(map, p);
+    conv_wg_kernel<AD, N, OUT, HS><<<grid, WG_THREADS, smem, stream>>>(map, p);
     return SN_OK;
 }
 
@@ -729,10 +778,10 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     dim3 grid((unsigned)std::min<long long>(p.n_tiles, n_sm));               // persistent, one CTA per SM (TMEM: 512 columns)
     const size_t smem = std::max(cfg.smem, (size_t)(227 * 1024 / 2) + 1);     // never two CTAs per SM: the second would spin in tcgen05.alloc
     rc = SN_ERR_INVALID;
-#define SN_WG_CASE(ad, nn) if (cfg.AD == ad && N == nn) rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nn, WG_OUT_WINO>(map, p, grid, smem, stream) \
-                                                                                         : wg_launch_t<ad, nn, WG_OUT_RAW>(map, p, grid, smem, stream)
-    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112) rc = wg_launch_t<1, 112, WG_OUT_FINAL>(map, p, grid, smem, stream); }
-    else { SN_WG_CASE(4, 32); SN_WG_CASE(2, 32); SN_WG_CASE(1, 80); SN_WG_CASE(1, 112); }
+#define SN_WG_CASE(ad, nn, geo8) if (cfg.AD == ad && N == nn && (p.hs != 0) == geo8) \
+        rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nn, WG_OUT_WINO, geo8>(map, p, grid, smem, stream) : wg_launch_t<ad, nn, WG_OUT_RAW, geo8>(map, p, grid, smem, stream)
+    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112 && !p.hs) rc = wg_launch_t<1, 112, WG_OUT_FINAL, false>(map, p, grid, smem, stream); }
+    else { SN_WG_CASE(4, 32, false); SN_WG_CASE(2, 32, false); SN_WG_CASE(1, 80, false); SN_WG_CASE(1, 112, false); SN_WG_CASE(1, 80, true); SN_WG_CASE(1, 112, true); }
 #undef SN_WG_CASE
     if (rc != SN_OK) { if (rc == SN_ERR_INVALID) set_error("conv_wg: no kernel instance for AD=%d N=%d", cfg.AD, N); return rc; }
     g_conv_path[2].fetch_add(1, std::memory_order_relaxed);

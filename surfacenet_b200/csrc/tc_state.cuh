@@ -61,4 +61,7 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
 int raw_to_wino_launch(const __half* in_raw, int n, int cg_in_total, int cg_in_off, int cg_count, int S, __half* out_wino, int cg_out_total,
                        int cg_out_off, cudaStream_t stream, int dil = 1);
 
+// fp32 NCDHW input (n, C <= 8, S^3) -> group 0 of a 2-group Winograd-domain tensor (conv1_1's operand)
+int pack_wino_launch(const float* x, int n, int C, int S, __half* out_wino, cudaStream_t stream);
+
 }  // namespace sn

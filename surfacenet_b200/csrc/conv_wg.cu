@@ -47,6 +47,7 @@ struct ConvWgParams {
     int TP, tp_shift, TH, HH, HD;   // pairs per row (= S/2), log2(TP), rows per tile (128 / TP), halo extents in h / d
     int NA, NB;                     // A ring stages, weight ring slots (3 taps per slot)
     int hs, d_step;                 // hs: S = 8 geometry (below); d_step: d-planes per tile (AD, or 4 in the hs geometry)
+    int d_fastest;                  // tile order (SN_WG_ORDER): 1 = d fastest, 0 = h fastest
     int dbg;                        // SN_WG_DEBUG (timing experiments only): 1 = no output stores, 2 = no output math after the drains
     int a_prec_bytes;               // bytes of one precision plane of one A stage = 2 groups * HD*HH*TP*16
     long long n_tiles;              // tiles_h * tiles_d * n_pc * n_ntiles; every tile = 4 frequency passes
@@ -66,8 +67,14 @@ struct WgTile { int nt, pc, d0, h0; };
 
 __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int AD) {
     WgTile c;
-    uint32_t q = t / (uint32_t)p.tiles_h; c.h0 = (int)(t - q * p.tiles_h) * p.TH; t = q;
-    q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * p.d_step; t = q;
+    uint32_t q;
+    if (p.d_fastest) {              // consecutive tiles (= concurrently running CTAs) walk the d axis: the 3-plane d halo is the larger overlap
+        q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * p.d_step; t = q;
+        q = t / (uint32_t)p.tiles_h; c.h0 = (int)(t - q * p.tiles_h) * p.TH; t = q;
+    } else {
+        q = t / (uint32_t)p.tiles_h; c.h0 = (int)(t - q * p.tiles_h) * p.TH; t = q;
+        q = t / (uint32_t)p.tiles_d; c.d0 = (int)(t - q * p.tiles_d) * p.d_step; t = q;
+    }
     q = t / (uint32_t)p.n_pc; c.pc = (int)(t - q * p.n_pc);
     c.nt = (int)q;
     return c;
@@ -742,6 +749,8 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.n_cblk = wu.n_cblk; p.cg_in = cg_in_total ? cg_in_total : wu.Cin_pad / 8;
     static const int env_dbg = getenv("SN_WG_DEBUG") ? atoi(getenv("SN_WG_DEBUG")) : 0;
     p.dbg = env_dbg;
+    static const int env_order = getenv("SN_WG_ORDER") ? atoi(getenv("SN_WG_ORDER")) : 1;       // measured: 67.4 vs 68.5 ms per C3 step
+    p.d_fastest = env_order;
     p.hs = (S == 8) ? 1 : 0;
     p.TP = S / 2; p.tp_shift = (p.TP == 4) ? 2 : (p.TP == 8) ? 3 : (p.TP == 16 ? 4 : 5); p.TH = p.hs ? 8 : 128 / p.TP;
     p.HH = p.hs ? 8 : p.TH + 2 * cu.dil; p.HD = (p.hs ? 4 : cfg.AD) + 2 * cu.dil; p.d_step = p.hs ? 4 : cfg.AD;

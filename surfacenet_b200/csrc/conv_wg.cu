@@ -81,7 +81,7 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 }
 
 // AD = d-planes per CTA, N = output channels of the N tile (padded to 16),
-// HS = the S = 8 geometry (compile time: its branches sit in the MMA issue loop, where every instruction counts),
+// PAIR = the last channel block pairs taps as K halves (conv1_1, merge_conv2) and HS = the S = 8 geometry (both compile time: its branches sit in the MMA issue loop, where every instruction counts),
 // OUT = output format of the unit (WG_OUT_*): a template parameter so that only ONE epilogue variant is in the instruction stream
 // (the first version carried all three, fully unrolled over the column chunks: 150 KB of straight-line code per tile, 23 % of the
 // stall samples were instruction-cache misses and the WINO units ran at half the speed of the RAW ones).
@@ -92,7 +92,7 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 // pipe in ONE fixed order (hi slot 0, lo slot 0, hi slot 1, ...) -> bit-reproducible results, and the pass-opening A_hi MMA
 // (accumulate = 0, it initialises the corr columns) is always ahead of the first A_lo MMA.  Each warp prepares its descriptors
 // while the other one issues; only the three UTCHMMA + the hand-off are serialised.
-template <int AD, int N, int OUT, bool HS>
+template <int AD, int N, int OUT, bool HS, bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p) {
     constexpr int TPS = 3;                                             // taps per weight slot: the three kh taps of one kd
@@ -205,7 +205,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         const uint32_t plane16 = (uint32_t)(p.HH * p.TP);
         const uint32_t kd_step = plane16 * (uint32_t)p.dil, kh_step = (uint32_t)(p.TP * p.dil);
         const uint32_t smA16 = (smem_u32(smA) >> 4) + (me ? ((uint32_t)p.a_prec_bytes >> 4) : 0u);   // the lo issuer reads the lo precision plane
-        if (p.pair_last) {                                                   // virtual tap v -> taps (2v, 2v+1) of the 9; beyond, the weights are zero
+        if (PAIR) {                                                   // virtual tap v -> taps (2v, 2v+1) of the 9; beyond, the weights are zero
             if (lane < 6) {
                 const int ta = min(2 * lane, 8), tb = min(2 * lane + 1, 8);
                 const uint32_t oa = (ta / 3) * kd_step + (ta % 3) * kh_step;
@@ -233,7 +233,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                     if (!HS) mbar_wait(&a_full[sa], pha);
                     tc_fence_after();
                     uint32_t a_base16 = smA16 + sa * a_stage16;
-                    const bool paired = p.pair_last && cb == p.n_cblk - 1;
+                    const bool paired = PAIR && cb == p.n_cblk - 1;
                     const int n_slots = paired ? 2 : 3;
                     uint32_t a_kd = a_base16 | a_lbo;
                     for (int sl = 0; sl < n_slots; ++sl, a_kd += kd_step, ++g) {
@@ -722,14 +722,14 @@ static WgCfg wg_config(int S, int N, int dil) {
     return c;
 }
 
-template <int AD, int N, int OUT, bool HS>
+template <int AD, int N, int OUT, bool HS, bool PAIR>
 static int wg_launch_t(const CUtensorMap& map, const ConvWgParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, N, OUT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, N, OUT, HS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
         attr_set = true;
     }
-    conv_wg_kernel<AD, N, OUT, HS><<<grid, WG_THREADS, smem, stream>>>(map, p);
+    conv_wg_kernel<AD, N, OUT, HS, PAIR><<<grid, WG_THREADS, smem, stream>>>(map, p);
     return SN_OK;
 }
 
@@ -787,10 +787,14 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     dim3 grid((unsigned)std::min<long long>(p.n_tiles, n_sm));               // persistent, one CTA per SM (TMEM: 512 columns)
     const size_t smem = std::max(cfg.smem, (size_t)(227 * 1024 / 2) + 1);     // never two CTAs per SM: the second would spin in tcgen05.alloc
     rc = SN_ERR_INVALID;
-#define SN_WG_CASE(ad, nn, geo8) if (cfg.AD == ad && N == nn && (p.hs != 0) == geo8) \
-        rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nn, WG_OUT_WINO, geo8>(map, p, grid, smem, stream) : wg_launch_t<ad, nn, WG_OUT_RAW, geo8>(map, p, grid, smem, stream)
-    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112 && !p.hs) rc = wg_launch_t<1, 112, WG_OUT_FINAL, false>(map, p, grid, smem, stream); }
-    else { SN_WG_CASE(4, 32, false); SN_WG_CASE(2, 32, false); SN_WG_CASE(1, 80, false); SN_WG_CASE(1, 112, false); SN_WG_CASE(1, 80, true); SN_WG_CASE(1, 112, true); }
+#define SN_WG_CASE(ad, nn, geo8, pr) if (cfg.AD == ad && N == nn && (p.hs != 0) == geo8 && (p.pair_last != 0) == pr) \
+        rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nn, WG_OUT_WINO, geo8, pr>(map, p, grid, smem, stream) : wg_launch_t<ad, nn, WG_OUT_RAW, geo8, pr>(map, p, grid, smem, stream)
+    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112 && !p.hs && p.pair_last) rc = wg_launch_t<1, 112, WG_OUT_FINAL, false, true>(map, p, grid, smem, stream); }
+    else {
+        SN_WG_CASE(4, 32, false, false); SN_WG_CASE(4, 32, false, true); SN_WG_CASE(2, 32, false, false); SN_WG_CASE(2, 32, false, true);
+        SN_WG_CASE(1, 80, false, false); SN_WG_CASE(1, 112, false, false); SN_WG_CASE(1, 112, false, true);
+        SN_WG_CASE(1, 80, true, false); SN_WG_CASE(1, 112, true, false);
+    }
 #undef SN_WG_CASE
     if (rc != SN_OK) { if (rc == SN_ERR_INVALID) set_error("conv_wg: no kernel instance for AD=%d N=%d", cfg.AD, N); return rc; }
     g_conv_path[2].fetch_add(1, std::memory_order_relaxed);

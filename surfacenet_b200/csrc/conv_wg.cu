@@ -40,6 +40,13 @@ constexpr int WG_THREADS = 640;        // warps: 0..15 epilogue, 16 A producer, 
 // control warpgroup (warps 16..19) gives registers back and the four epilogue warpgroups take them: 128 * 56 + 512 * 104 = 60,416.
 // (112 for the epilogue deadlocks in setmaxnreg.inc: 62,464 > 61,440.)
 constexpr int WG_CTRL_REGS = 56, WG_EPI_REGS = 104;
+#ifndef SN_WG_ISSUERS
+#define SN_WG_ISSUERS 1
+#endif
+// MMA-issuing warps.  2 = the A_hi / A_lo products from two warps handing a token back and forth: measured NOT bit-reproducible (the two warps sit on
+// different SMSPs; the order in which their MMAs reach the tensor pipe is not the order of issue: 0.1 % of the outputs differ by 1-2 ulp from run to
+// run).  1 = one warp issues everything: one order by construction.
+constexpr int WG_NI = SN_WG_ISSUERS;
 constexpr int WG_MAX_NA = 4, WG_MAX_NB = 8;
 constexpr int WG_MAX_C = 320;          // output channels of a unit, padded (conv4: 4 x 80)
 
@@ -97,6 +104,10 @@ template <int AD, int N, int OUT, bool HS, bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p) {
     constexpr int TPS = 3;                                             // taps per weight slot: the three kh taps of one kd
+    // MMA issuers: SPLIT_PROD (SN_WG_ISSUERS=2, not bit-reproducible) = warp 18 the A_hi products, warp 19 the A_lo products; otherwise every
+    // accumulator has ONE issuer: a single warp when AD = 1, two warps owning the even / odd d-planes when AD >= 2 (conv1_x)
+    constexpr bool SPLIT_PROD = (WG_NI == 2);
+    constexpr int NI = SPLIT_PROD ? 2 : ((AD >= 2) ? 2 : 1);
     constexpr int NQ = (N / 8 + 3) / 4;                                // 8-column chunks per epilogue warp and plane (4 column quarters)
     constexpr int NCH = AD * NQ;                                       // chunks (16 registers each) per epilogue thread
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -122,9 +133,9 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
     const uint32_t n_tiles = (uint32_t)p.n_tiles;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
-        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 2); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 512); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], NI); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], NI); mbar_init(&acc_empty[i], 512); }
         mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);            // the issue-order tokens
         // the hi issuer owns the token at the start: phase 0 of its barrier is completed here
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[1])) : "memory");
@@ -195,7 +206,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 }
             }
         }
-    } else if (warp == 18 || warp == 19) {
+    } else if (warp == 18 || (warp == 19 && NI == 2)) {
         // ===== MMA issuers: warp 18 = A_hi * [W_hi ; W_lo]^T -> [main | corr], warp 19 = A_lo * W_hi^T -> corr; converged warp, one elected lane =====
         const int me = warp - 18;
         const uint32_t ab_hi32 = 8u | (1u << 14);                            // SBO = 128 B (rows are 16 B apart, linearly), descriptor version 1
@@ -205,7 +216,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         const uint32_t b_slot16 = b_slot_bytes >> 4;
         const uint32_t plane16 = (uint32_t)(p.HH * p.TP);
         const uint32_t kd_step = plane16 * (uint32_t)p.dil, kh_step = (uint32_t)(p.TP * p.dil);
-        const uint32_t smA16 = (smem_u32(smA) >> 4) + (me ? ((uint32_t)p.a_prec_bytes >> 4) : 0u);   // the lo issuer reads the lo precision plane
+        const uint32_t smA16 = (smem_u32(smA) >> 4) + ((SPLIT_PROD && me) ? ((uint32_t)p.a_prec_bytes >> 4) : 0u);   // product split: the lo issuer reads the lo precision plane
         if (PAIR) {                                                   // virtual tap v -> taps (2v, 2v+1) of the 9; beyond, the weights are zero
             if (lane < 6) {
                 const int ta = min(2 * lane, 8), tb = min(2 * lane + 1, 8);
@@ -221,15 +232,17 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
             const int Nc = p.nt_nc[c.nt];                                    // rows of W_hi before W_lo = column of the correction accumulator
             const int R = 2 * Nc;
             // D = f32, A = B = f16, K-major, M = 128; hi issuer: N' = 2 Nc columns from column 0, lo issuer: N columns from column Nc
-            const uint32_t idesc = (1u << 4) | ((uint32_t)((me ? N : R) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(((SPLIT_PROD && me) ? N : R) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc_lo = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);      // single issuer: the A_lo product
+            const uint32_t a_prec16 = (uint32_t)p.a_prec_bytes >> 4;
             const uint32_t b_lbo = (uint32_t)R << 16;
             const uint32_t tapB16 = (uint32_t)(2 * R);
             for (int f = 0; f < 4; ++f, ++j) {
                 const uint32_t buf = j & 1, use = j >> 1;
-                const uint32_t dbase = tmem_base + buf * buf_cols + (me ? (uint32_t)Nc : 0u);
+                const uint32_t dbase = tmem_base + buf * buf_cols + ((SPLIT_PROD && me) ? (uint32_t)Nc : 0u);
                 mbar_wait(&acc_empty[buf], (use & 1) ^ 1);                   // the epilogue has drained the previous pass of this set
                 tc_fence_after();
-                uint32_t acc_flag = me ? 1u : 0u;
+                uint32_t acc_flag = (SPLIT_PROD && me) ? 1u : 0u;
                 // one channel block = 3 ring slots of 3 taps (2 slots of tap PAIRS for a paired last block).  The paired variant is a second
                 // instantiation of the block body so that the common one carries no table look-ups / selects (every instruction of this loop
                 // is on the critical path of the tensor pipe: the run-time `paired` select cost 4.5 % of the whole step)
@@ -247,7 +260,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                             a_kd = a_base16 | a_lbo;
                         }
                         mbar_wait(&b_full[sb], phb);
-                        mbar_wait(&tok[me ^ 1], g & 1);                        // my turn: hi issuer after lo(g-1) (phase 0: the initial token), lo issuer after hi(g)
+                        if (SPLIT_PROD) mbar_wait(&tok[me ^ 1], g & 1);        // my turn: hi issuer after lo(g-1) (phase 0: the initial token), lo issuer after hi(g)
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t b_lo32 = (smB16 + sb * b_slot16) | b_lbo;
@@ -257,12 +270,21 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                                 const uint64_t db = ((uint64_t)ab_hi32 << 32) | (b_lo32 + kk * tapB16);
 #pragma unroll
                                 for (int a = 0; a < AD; ++a) {
+                                    if (!SPLIT_PROD && NI == 2 && (a & 1) != me) continue;        // plane split: this warp owns the planes a % 2 == me
                                     const uint64_t da = ((uint64_t)ab_hi32 << 32) | (a_tap + a * plane16);
                                     tc_mma(dbase + (uint32_t)(a * 2 * N), da, db, idesc, acc_flag);
                                 }
+                                if (!SPLIT_PROD) {                               // the A_lo * W_hi product: same weights, N rows, corr columns
+#pragma unroll
+                                    for (int a = 0; a < AD; ++a) {
+                                        if (NI == 2 && (a & 1) != me) continue;
+                                        const uint64_t da = ((uint64_t)ab_hi32 << 32) | (a_tap + a_prec16 + a * plane16);
+                                        tc_mma(dbase + (uint32_t)(a * 2 * N + Nc), da, db, idesc_lo, 1u);
+                                    }
+                                }
                                 acc_flag = 1u;
                             }
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[me])) : "memory");   // pass the token
+                            if (SPLIT_PROD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[me])) : "memory");   // pass the token
                             tc_commit(&b_empty[sb]);
                         }
                         __syncwarp();
@@ -287,7 +309,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp < 16) {
         // ===== epilogue: warps 0..15.  TMEM lane quarter q = warp % 4 (rows m = 32 q + lane = pair (h0 + m / TP, t = m % TP)), column quarter
         //       cq = warp / 4: NQ chunks of 8 accumulator columns per plane, [cq*NQ*8, +NQ*8) clipped to N =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WG_EPI_REGS));

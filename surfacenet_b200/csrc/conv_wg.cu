@@ -20,8 +20,8 @@
 // TMEM: every frequency needs its own [main | corr] accumulator pair (2N columns, conv_tc.cu) and only 512 columns exist, so the four
 // frequencies of a tile are four consecutive passes over the K loop (each streams ITS OWN transformed tile: no operand is read twice)
 // into two alternating accumulator sets; the epilogue drains set f while set f+1 is being computed and keeps the partial output
-// transform (P0 = M0+M1+M2 so far, P1 = M1-M2-M3 so far) in registers -- 2*N values per pair, split over TWO epilogue warps per TMEM
-// lane quarter (8 epilogue warps, each N/2 columns).  After the fourth pass: folded BatchNorm + ReLU, then either the next unit's
+// transform (P0 = M0+M1+M2 so far, P1 = M1-M2-M3 so far) in registers -- 2*N values per pair, split over FOUR epilogue warps per TMEM
+// lane quarter (16 epilogue warps, each <= 32 columns).  After the fourth pass: folded BatchNorm + ReLU, then either the next unit's
 // input transform (neighbours by shuffle) + hi/lo split -> wino blk, or raw blk (pool / 1x1x1 consumers), or the fused merge_conv3.
 //
 // Round-toward-zero accumulation: each accumulator now sees 9*C_in/16 accumulating MMAs instead of 27*C_in/16, and all four
@@ -93,13 +93,11 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 // OUT = output format of the unit (WG_OUT_*): a template parameter so that only ONE epilogue variant is in the instruction stream
 // (the first version carried all three, fully unrolled over the column chunks: 150 KB of straight-line code per tile, 23 % of the
 // stall samples were instruction-cache misses and the WINO units ran at half the speed of the RAW ones).
-// Warps: 0..15 epilogue, 16 A producer, 17 B producer, 18 issues the A_hi MMAs, 19 the A_lo MMAs (+ TMEM allocation).  One warp's instruction
-// stream (~15 dependent instructions per MMA: descriptor words through R2UR) cannot feed the tensor pipe at 160 cycles per tap with a
-// single CTA per SM, hence two issuers.  Both add into the corr columns, and fp32 accumulation with truncation is not associative, so the
-// two warps hand a token back and forth (tok[1]: the hi issuer may issue slot g, tok[0]: the lo issuer may issue slot g): the MMAs enter the tensor
-// pipe in ONE fixed order (hi slot 0, lo slot 0, hi slot 1, ...) -> bit-reproducible results, and the pass-opening A_hi MMA
-// (accumulate = 0, it initialises the corr columns) is always ahead of the first A_lo MMA.  Each warp prepares its descriptors
-// while the other one issues; only the three UTCHMMA + the hand-off are serialised.
+// Warps: 0..15 epilogue, 16 A producer, 17 B producer, 18 (+ 19 when AD >= 2) MMA issuer, 19 TMEM allocation.  The issue loop is the critical path
+// of the kernel (one CTA per SM: nothing else hides its latency), hence the compile-time variants above.  Every accumulator has ONE issuing
+// warp -- both products of the split for all planes (AD = 1) or for the planes a % 2 == warp - 18 (AD >= 2) -- so the accumulation order
+// is fixed and the results are bit-reproducible.  SN_WG_ISSUERS=2 (compile time) splits the A_hi / A_lo products over the two warps with a
+// token handed back and forth per slot (tok[]): 3.4 % faster, NOT reproducible (see WG_NI above).
 template <int AD, int N, int OUT, bool HS, bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p) {

@@ -22,7 +22,8 @@ static int infer_enqueue(const sn_net* h, const uint8_t* images_dev, const int64
                          int n_views, const double* P_dev, const float* xyz_dev, const float* resol_dev,
                          const int32_t* viewpairs_dev, const float* w_dev, int n_cubes, int n_vp, int D, float min_prob_f16,
                          float* fused_out_dev, float* unfused_out_dev, void* pred16_out_dev, uint8_t* votes_out_dev,
-                         void* workspace_dev, int64_t workspace_bytes, int mode, void* stream, int32_t** rp_flags) {
+                         void* workspace_dev, int64_t workspace_bytes, int mode, void* stream, int32_t** rp_flags,
+                         cudaEvent_t pred_ready = nullptr, bool keep_X = false) {
     SN_CHECK_ARG(h && images_dev && img_offset_dev && img_hw_dev && P_dev && xyz_dev && resol_dev && viewpairs_dev && fused_out_dev,
                  "sn_infer_batch: NULL argument");
     SN_CHECK_ARG(!votes_out_dev || pred16_out_dev, "sn_infer_batch: votes need the float16 prediction buffer");
@@ -37,18 +38,27 @@ static int infer_enqueue(const sn_net* h, const uint8_t* images_dev, const int64
     const int64_t ws2_bytes = workspace_bytes - xb;
     const int64_t V = (int64_t)D * D * D;
     int rc;
-    // main_reconstruct.py:134-143: CVC.gen_coloredCubes + preprocess_augmentation (mean subtraction only)
-    rc = sn_cvc_gather(images_dev, img_offset_dev, img_hw_dev, n_views, P_dev, xyz_dev, resol_dev, viewpairs_dev, n_cubes, n_vp, D,
-                       h->net.mean6, X, nullptr, nullptr, nullptr, stream);
-    if (rc != SN_OK) return rc;
-    // main_reconstruct.py:145-146: nViewPair_SurfaceNet_fn(X[, w])
-    rc = sn_net_forward(h, X, n_cubes, n_vp, D, w_dev, fused_out_dev, unfused_out_dev, ws2, ws2_bytes, mode, stream);
-    if (rc != SN_OK) return rc;
+    if (!keep_X && tc_gathers_directly(h->net, D, mode)) {
+        // main_reconstruct.py:134-146 in one chain: the network's first pass colours its own operand (conv_wg.cu:cvc_wino_kernel), no fp32 X
+        SN_CHECK_ARG(n_views >= 1 && (int64_t)n_cubes * n_vp <= (1 << 28), "sn_infer_batch: bad sizes (n_cubes=%d n_vp=%d n_views=%d)", n_cubes, n_vp, n_views);
+        const CvcSource src{images_dev, img_offset_dev, img_hw_dev, n_views, P_dev, xyz_dev, resol_dev, viewpairs_dev, n_vp, h->net.mean6};
+        rc = net_forward(h, nullptr, &src, n_cubes, n_vp, D, w_dev, fused_out_dev, unfused_out_dev, ws2, ws2_bytes, mode, stream);
+        if (rc != SN_OK) return rc;
+    } else {
+        // main_reconstruct.py:134-143: CVC.gen_coloredCubes + preprocess_augmentation (mean subtraction only)
+        rc = sn_cvc_gather(images_dev, img_offset_dev, img_hw_dev, n_views, P_dev, xyz_dev, resol_dev, viewpairs_dev, n_cubes, n_vp, D,
+                           h->net.mean6, X, nullptr, nullptr, nullptr, stream);
+        if (rc != SN_OK) return rc;
+        // main_reconstruct.py:145-146: nViewPair_SurfaceNet_fn(X[, w])
+        rc = sn_net_forward(h, X, n_cubes, n_vp, D, w_dev, fused_out_dev, unfused_out_dev, ws2, ws2_bytes, mode, stream);
+        if (rc != SN_OK) return rc;
+    }
     if (pred16_out_dev) {
         // utils/sparseCubes.py:115: prediction_sub.astype(np.float16)
         rc = sn_cast_f32_to_f16(fused_out_dev, (int64_t)n_cubes * V, pred16_out_dev, stream);
         if (rc != SN_OK) return rc;
     }
+    if (pred_ready) SN_CUDA(cudaEventRecord(pred_ready, (cudaStream_t)stream));     // the probabilities are final: ray pooling only reads them
     if (votes_out_dev) {
         // utils/sparseCubes.py:57-62: rayPooling_1cube_numpy(..., prediction_thresh=min_prob) per cube
         rc = raypool_enqueue(pred16_out_dev, 1, 1, min_prob_f16, viewpairs_dev, P_dev, n_views, xyz_dev, resol_dev, n_cubes, n_vp, D,
@@ -69,6 +79,24 @@ extern "C" int sn_infer_batch(const sn_net* h, const uint8_t* images_dev, const 
                            workspace_dev, workspace_bytes, mode, stream, &flags);
     if (rc != SN_OK) return rc;
     return flags ? raypool_check(flags, stream) : SN_OK;
+}
+
+// D2H side stream of the host-buffer entry: the probability volumes (6 of the 7 result bytes per voxel) leave the device while ray pooling
+// still runs on the caller's stream.  One per device, created on first use.
+struct HostCopyLane { cudaStream_t st = nullptr; cudaEvent_t ready = nullptr, done = nullptr; };
+static int host_copy_lane(HostCopyLane** out) {
+    static HostCopyLane lanes[64];
+    int dev = 0;
+    SN_CUDA(cudaGetDevice(&dev));
+    SN_CHECK_ARG(dev >= 0 && dev < 64, "sn_infer_batch_host: device ordinal %d", dev);
+    HostCopyLane& l = lanes[dev];
+    if (!l.st) {
+        SN_CUDA(cudaEventCreateWithFlags(&l.ready, cudaEventDisableTiming));
+        SN_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        SN_CUDA(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+    }
+    *out = &l;
+    return SN_OK;
 }
 
 extern "C" int sn_infer_batch_host(const sn_net* h, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
@@ -102,12 +130,22 @@ extern "C" int sn_infer_batch_host(const sn_net* h, const uint8_t* images_dev, c
     if (w_host) SN_CUDA(cudaMemcpyAsync(w_d, w_host, (int64_t)n_cubes * n_vp * 4, cudaMemcpyHostToDevice, st));
     int32_t* flags = nullptr;
     const bool want16 = pred16_out_host || votes_out_host;
+    // with ray pooling requested, the probability copies run on the side stream under the ray-pool kernels (the staging buffers sit
+    // behind the inner workspace, which ray pooling reuses, so nothing they read is overwritten)
+    HostCopyLane* lane = nullptr;
+    if (votes_out_host && (fused_out_host || pred16_out_host)) { int lrc = host_copy_lane(&lane); if (lrc != SN_OK) return lrc; }
     int rc = infer_enqueue(h, images_dev, img_offset_dev, img_hw_dev, n_views, P_dev, xyz_d, resol_d, vp_d, w_host ? w_d : nullptr,
                            n_cubes, n_vp, D, min_prob_f16, fused_d, nullptr, want16 ? p16_d : nullptr, votes_out_host ? votes_d : nullptr,
-                           workspace_dev, inner, mode, stream, &flags);
+                           workspace_dev, inner, mode, stream, &flags, lane ? lane->ready : nullptr);
     if (rc != SN_OK) return rc;
-    if (fused_out_host) SN_CUDA(cudaMemcpyAsync(fused_out_host, fused_d, n_cubes * V * 4, cudaMemcpyDeviceToHost, st));
-    if (pred16_out_host) SN_CUDA(cudaMemcpyAsync(pred16_out_host, p16_d, n_cubes * V * 2, cudaMemcpyDeviceToHost, st));
+    const cudaStream_t cst = lane ? lane->st : st;
+    if (lane) SN_CUDA(cudaStreamWaitEvent(lane->st, lane->ready, 0));
+    if (fused_out_host) SN_CUDA(cudaMemcpyAsync(fused_out_host, fused_d, n_cubes * V * 4, cudaMemcpyDeviceToHost, cst));
+    if (pred16_out_host) SN_CUDA(cudaMemcpyAsync(pred16_out_host, p16_d, n_cubes * V * 2, cudaMemcpyDeviceToHost, cst));
+    if (lane) {
+        SN_CUDA(cudaEventRecord(lane->done, lane->st));
+        SN_CUDA(cudaStreamWaitEvent(st, lane->done, 0));                        // the caller's stream (synchronised below) covers both
+    }
     if (votes_out_host) SN_CUDA(cudaMemcpyAsync(votes_out_host, votes_d, n_cubes * V, cudaMemcpyDeviceToHost, st));
     if (flags) return raypool_check(flags, stream);
     SN_CUDA(cudaStreamSynchronize(st));
@@ -154,7 +192,8 @@ extern "C" int sn_infer_batch_sparse(const sn_net* h, const uint8_t* images_dev,
     const int64_t V = (int64_t)D * D * D;
     int32_t* flags = nullptr;
     int rc = infer_enqueue(h, images_dev, img_offset_dev, img_hw_dev, n_views, P_dev, xyz_dev, resol_dev, viewpairs_dev, w_dev, n_cubes, n_vp, D,
-                           min_prob_f16, fused, n_vp > 1 ? unf : nullptr, p16, votes, workspace_dev, off[0], mode, stream, &flags);
+                           min_prob_f16, fused, n_vp > 1 ? unf : nullptr, p16, votes, workspace_dev, off[0], mode, stream, &flags, nullptr,
+                           /*keep_X: the colours below are read from it*/ true);
     if (rc != SN_OK) return rc;
     // main_reconstruct.py:150-152: colours = mean-subtracted CVC (head of the workspace) + mean, fused with w * unfused p
     const float* X = (const float*)workspace_dev;

@@ -676,6 +676,101 @@ side_wino_kernel(const __half* __restrict__ in, const float* __restrict__ Wt, co
     }
 }
 
+// side_wino_kernel and the 2^3 max pool that follows conv1_3 (nets/SurfaceNet.py:37-38) in ONE pass over conv1_3's output: both read the
+// same raw blk tensor (4 B per voxel-channel, the largest activation of the network), so the pool's separate read is dropped.  One thread per
+// POOLED voxel's w-pair column: the four (d, h) rows of its 2^3 window one after the other -- 1x1x1 unit + sigmoid + input transform of the row's
+// output pair exactly as side_wino_kernel (same FMA order: bit-identical), the window maximum kept per channel as pool_blk_kernel does.
+template <int CG_IN>
+__global__ void __launch_bounds__(256)
+side_pool_wino_kernel(const __half* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ scale, const float* __restrict__ shift,
+                      int S, long long total, __half* __restrict__ out, int cg_total, int cg_off, __half* __restrict__ pooled) {
+    __shared__ float sW[CG_IN * 8 * 16];                                     // [c_in][16 outputs]
+    __shared__ float sS[32];
+    for (int i = threadIdx.x; i < CG_IN * 8 * 16; i += blockDim.x) sW[i] = Wt[i];
+    if (threadIdx.x < 16) { sS[threadIdx.x] = scale[threadIdx.x]; sS[16 + threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+    const int TP = S / 2, So = S / 2;
+    const long long vol = (long long)S * S * S, volw = vol / 2, volo = vol / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((total + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+        const bool active = i < total;                                       // total = n * So * So * TP
+        const long long ii = active ? i : total - 1;
+        const int tt = (int)(ii % TP);
+        const long long orow = ii / TP;                                      // (n, od, oh)
+        const int oh = (int)(orow % So), od = (int)((orow / So) % So);
+        const long long n = orow / ((long long)So * So);
+        const bool first_t = tt == 0, last_t = tt == TP - 1;
+        float m[CG_IN][8];
+#pragma unroll
+        for (int g = 0; g < CG_IN; ++g)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[g][k] = -INFINITY;
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+            const long long dh = (long long)(2 * od + (r >> 1)) * S + 2 * oh + (r & 1);
+            float acc[2][16];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int o = 0; o < 16; ++o) acc[e][o] = 0.f;
+#pragma unroll
+            for (int g = 0; g < CG_IN; ++g) {
+                const __half* src = in + ((n * 2) * CG_IN + g) * vol * 8 + (dh * S + 2 * tt) * 8;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float v[8];
+                    load_blk8(src + e * 8, (long long)CG_IN * vol * 8, 2, v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        m[g][k] = fmaxf(m[g][k], v[k]);
+                        const float4* w4 = reinterpret_cast<const float4*>(sW + (g * 8 + k) * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 w = w4[q];
+                            acc[e][4 * q + 0] = fmaf(v[k], w.x, acc[e][4 * q + 0]); acc[e][4 * q + 1] = fmaf(v[k], w.y, acc[e][4 * q + 1]);
+                            acc[e][4 * q + 2] = fmaf(v[k], w.z, acc[e][4 * q + 2]); acc[e][4 * q + 3] = fmaf(v[k], w.w, acc[e][4 * q + 3]);
+                        }
+                    }
+                }
+            }
+            const long long pos = dh * TP + tt;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float y[2][8];
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) y[e][k] = 1.f / (1.f + expf(-fmaf(acc[e][8 * g + k], sS[8 * g + k], sS[16 + 8 * g + k])));
+                uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    float v[2][4];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        float l = __shfl_up_sync(0xffffffffu, y[1][q + e], 1), rr = __shfl_down_sync(0xffffffffu, y[0][q + e], 1);
+                        l = first_t ? 0.f : l; rr = last_t ? 0.f : rr;
+                        v[e][0] = l - y[1][q + e]; v[e][1] = y[0][q + e] + y[1][q + e]; v[e][2] = y[1][q + e] - y[0][q + e]; v[e][3] = y[0][q + e] - rr;
+                    }
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) split_pack(v[0][f], v[1][f], hi[f][q >> 1], lo[f][q >> 1]);
+                }
+                if (active) {
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        __half* dst = out + (((n * 2) * 4 + f) * cg_total + cg_off + g) * volw * 8 + pos * 8;
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[f][0], hi[f][1], hi[f][2], hi[f][3]);
+                        *reinterpret_cast<uint4*>(dst + 4LL * cg_total * volw * 8) = make_uint4(lo[f][0], lo[f][1], lo[f][2], lo[f][3]);
+                    }
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int g = 0; g < CG_IN; ++g)
+                store_blk8(pooled + ((n * 2) * CG_IN + g) * volo * 8 + (((long long)od * So + oh) * So + tt) * 8, (long long)CG_IN * volo * 8, 2, m[g]);
+        }
+    }
+}
+
 static inline int ew_blocks(long long total) { return (int)std::min<long long>(cdiv(total, 256), 148 * 16); }
 
 // ------------------------------------------------------------------------------------------------
@@ -1072,6 +1167,20 @@ static int side_wino_launch(const Net& net, const __half* in, int n, int S, __ha
     return SN_OK;
 }
 
+// side_op1 -> Winograd-domain concat[0:16] AND the 2^3 max pool of the same input -> raw blk `pooled` (n, 2, 4, (S/2)^3, 8), one pass
+static int side_pool_wino_launch(const Net& net, const __half* in, int n, int S, __half* out, int cg_total, int cg_off, __half* pooled, cudaStream_t st) {
+    const TcState* ts = (const TcState*)net.tc;
+    const ConvUnit& su = net.units[U_SIDE1];
+    SN_CHECK_ARG(ts->units[U_SIDE1].side_w && su.Cin == 32 && su.Cout == 16 && (S == 16 || S == 32 || S == 64), "side_op1 + pool (Winograd layout): unsupported shape");
+    const long long total = (long long)n * (S / 2) * (S / 2) * (S / 2);
+    if (!total) return SN_OK;
+    prof_begin(U_SIDE1, st);
+    side_pool_wino_kernel<4><<<ew_blocks(total), 256, 0, st>>>(in, ts->units[U_SIDE1].side_w, su.scale, su.shift, S, total, out, cg_total, cg_off, pooled);
+    prof_end(U_SIDE1, st);
+    SN_LAUNCHED();
+    return SN_OK;
+}
+
 // halfs of workspace per pair-cube (per precision plane)
 static long long tc_halfs_per_pc(int D) {
     const long long V = (long long)D * D * D, V2 = V / 8, V4 = V / 64;
@@ -1198,7 +1307,8 @@ static int tc_forward_chunk(const Net& net, const float* X, int n, int D, float*
 // The forward graph with Winograd levels (exact mode).  Per level: raw blk input -> input transform (raw_to_wino) -> the 3x3x3 chain
 // in the Winograd domain (every unit's epilogue emits the next unit's transformed input) -> the last unit of the level writes raw blk for
 // its pool / side-output consumers.  Levels whose size has no Winograd instance run the direct kernels.
-static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, float* prob_out, __half* ws, const WgLevels& lv, cudaStream_t st) {
+static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, float* prob_out, __half* ws, const WgLevels& lv, cudaStream_t st,
+                               const CvcSource* src = nullptr, int pc0 = 0) {
     constexpr int P = 2;
     const long long V = (long long)D * D * D, np = (long long)n * P;
     const int S1 = D, S2 = D / 2, S4 = D / 4;
@@ -1215,7 +1325,8 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
 #define CONV(u, in, S, out, cgt, cgo) RUN(conv_tc_launch(net, u, in, n, S, P, EPI_BLK, out, cgt, cgo, nullptr, st))
 #define WCONV(u, in, S, fmt, out, cgt) do { prof_begin(u, st); rc = wg_conv_launch(net, u, in, n, S, fmt, out, cgt, 0, prob_out, st); prof_end(u, st); if (rc != SN_OK) return rc; } while (0)
     if (lv.l[0] && ((TcState*)net.tc)->wg[U_CONV1_1].pair_last) {
-        RUN(pack_wino_launch(X, n, 6, S1, x0w, st));                                    // X fp32 -> conv1_1's Winograd-domain operand in one pass
+        if (src) RUN(cvc_wino_launch(*src, pc0, n, S1, x0w, st));                       // images -> conv1_1's Winograd-domain operand (no fp32 X)
+        else RUN(pack_wino_launch(X, n, 6, S1, x0w, st));                               // X fp32 -> conv1_1's Winograd-domain operand in one pass
         WCONV(U_CONV1_1, x0w, S1, WG_OUT_WINO, a1w, 4);
         WCONV(U_CONV1_2, a1w, S1, WG_OUT_WINO, a2w, 4);
         WCONV(U_CONV1_3, a2w, S1, WG_OUT_RAW, a1, 4);
@@ -1223,9 +1334,14 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
         RUN(pack_launch(X, n, 6, 16, P, V, x0, st));
         CONV(U_CONV1_1, x0, S1, a1, 4, 0); CONV(U_CONV1_2, a1, S1, a2, 4, 0); CONV(U_CONV1_3, a2, S1, a1, 4, 0);
     }
-    if (lv.l[0]) RUN(side_wino_launch(net, a1, n, S1, catw, 8, 0, st));                 // side_op1 -> Winograd-domain concat[0:16] (catw = the dead x0w|a1w|a2w region)
-    else CONV(U_SIDE1, a1, S1, cat, 8, 0);                                             // side_op1 -> concat[0:16]
-    RUN(pool_launch(a1, n, 32, P, S1, p1, st));
+    static const bool side_pool = getenv("SN_SIDE_POOL") ? atoi(getenv("SN_SIDE_POOL")) != 0 : true;       // SN_SIDE_POOL=0: A/B against the two passes
+    if (lv.l[0] && side_pool) {
+        RUN(side_pool_wino_launch(net, a1, n, S1, catw, 8, 0, p1, st));                 // side_op1 -> Winograd-domain concat[0:16] + pool1, one read of conv1_3's output
+    } else {
+        if (lv.l[0]) RUN(side_wino_launch(net, a1, n, S1, catw, 8, 0, st));             // side_op1 -> Winograd-domain concat[0:16] (catw = the dead x0w|a1w|a2w region)
+        else CONV(U_SIDE1, a1, S1, cat, 8, 0);                                         // side_op1 -> concat[0:16]
+        RUN(pool_launch(a1, n, 32, P, S1, p1, st));
+    }
     if (lv.l[1]) {
         RUN(raw_to_wino_launch(p1, n, 4, 0, 4, S2, p1w, 4, 0, st));
         WCONV(U_CONV2_1, p1w, S2, WG_OUT_WINO, b1w, 10);
@@ -1277,8 +1393,18 @@ static int tc_forward_chunk_wg(const Net& net, const float* X, int n, int D, flo
     return SN_OK;
 }
 
-int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out, void* ws, int64_t ws_bytes, int mode, cudaStream_t st) {
+// the forward of (D, mode) starts with pack_wino (X -> conv1_1's Winograd operand): that pass can colour the operand itself
+bool tc_gathers_directly(const Net& net, int D, int mode) {
+    static const bool env_on = getenv("SN_CVC_FUSED") ? atoi(getenv("SN_CVC_FUSED")) != 0 : true;      // SN_CVC_FUSED=0: A/B against the two-pass form
+    if (!env_on || mode != SN_MODE_TC_EXACT || !net.tc) return false;
+    return wg_levels(net, D, 2).l[0] && ((TcState*)net.tc)->wg[U_CONV1_1].pair_last;
+}
+
+int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out, void* ws, int64_t ws_bytes, int mode, cudaStream_t st,
+               const CvcSource* src) {
     const int P = (mode == SN_MODE_TC_EXACT) ? 2 : 1;
+    if (src && !tc_gathers_directly(net, D, mode)) { set_error("tensor-core forward: no fused CVC gather for cube size %d in mode %d", D, mode); return SN_ERR_INVALID; }
+    if (!src && !X) { set_error("tensor-core forward: no input"); return SN_ERR_INVALID; }
     const int64_t need = tc_workspace_bytes(net, n_pc, D, mode);
     if (!ws || ws_bytes < need) { set_error("tensor-core forward: workspace %lld B < %lld B", (long long)ws_bytes, (long long)need); return SN_ERR_NOMEM; }
     const long long V = (long long)D * D * D;
@@ -1287,8 +1413,9 @@ int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out,
     for (int i = 0; i < n_pc; i += chunk) {
         const int n = std::min(chunk, n_pc - i);
         const WgLevels lv = wg_levels(net, D, P);
-        int rc = lv.any() ? tc_forward_chunk_wg(net, X + (long long)i * 6 * V, n, D, prob_out + (long long)i * V, w, lv, st)
-                          : tc_forward_chunk(net, X + (long long)i * 6 * V, n, D, prob_out + (long long)i * V, w, P, st);
+        const float* Xi = X ? X + (long long)i * 6 * V : nullptr;
+        int rc = lv.any() ? tc_forward_chunk_wg(net, Xi, n, D, prob_out + (long long)i * V, w, lv, st, src, i)
+                          : tc_forward_chunk(net, Xi, n, D, prob_out + (long long)i * V, w, P, st);
         if (rc != SN_OK) return rc;
     }
     return SN_OK;

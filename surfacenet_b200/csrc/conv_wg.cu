@@ -28,6 +28,7 @@
 // frequencies see the same number, so the relative compensation folded into the BatchNorm scale carries over unchanged.
 #include "tc_ptx.cuh"
 #include "tc_state.cuh"
+#include "geometry.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <type_traits>
@@ -588,6 +589,91 @@ pack_wino_kernel(const float* __restrict__ x, int C, int S, long long total, __h
             }
         }
     }
+}
+
+// K1 fused with the pack: the mean-subtracted CVC of pair-cubes [pc0, pc0 + n) (utils/CVC.py:6-53,104-111; the arithmetic of
+// cvc.cu:cvc_gather_kernel operation by operation: fp64 projection, rint, int32 index, scope mask, 1-tap gather, fp32 `rgb - mean`)
+// written straight as conv1_1's Winograd-domain operand -- bit-identical to cvc_gather_kernel + pack_wino_kernel without the fp32 X
+// round trip.  One thread per output pair (voxels w = 2t, 2t+1 of both views of the pair-cube); neighbours from the adjacent lanes.
+__global__ void __launch_bounds__(256)
+cvc_wino_kernel(const uint8_t* __restrict__ images, const int64_t* __restrict__ img_offset, const int32_t* __restrict__ img_hw, int n_views,
+                const double* __restrict__ P, const float* __restrict__ xyz, const float* __restrict__ resol, const int32_t* __restrict__ views,
+                int n_vp, const float* __restrict__ mean6, int pc0, int S, long long total, __half* __restrict__ out) {
+    const int TP = S / 2;
+    const long long vol = (long long)S * S * S, volw = vol / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ((total + 31) & ~31LL); i += (long long)gridDim.x * blockDim.x) {
+        const bool active = i < total;
+        const long long ii = active ? i : total - 1;
+        const int t = (int)(ii % TP);
+        const long long row = ii / TP;                                       // (n, d, h)
+        const long long n = row / ((long long)S * S), dh = row % ((long long)S * S);
+        const int d = (int)(dh / S), h = (int)(dh % S);
+        const long long pc = pc0 + n;
+        const int b = (int)(pc / n_vp);
+        const float rs = __ldg(resol + b);
+        const double cx = voxel_coord(d, rs, __ldg(xyz + 3 * b)), cy = voxel_coord(h, rs, __ldg(xyz + 3 * b + 1));
+        const float z0 = __ldg(xyz + 3 * b + 2);
+        const bool first_t = t == 0, last_t = t == TP - 1;
+        float v[4][8];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) { v[f][6] = 0.f; v[f][7] = 0.f; }
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int view = __ldg(views + 2 * pc + side);
+            const bool view_ok = (view >= 0 && view < n_views);
+            float y[2][3];                                                    // [voxel of the pair][r, g, b], 0 outside the image (CVC.py:42-46)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) { y[e][0] = 0.f; y[e][1] = 0.f; y[e][2] = 0.f; }
+            if (view_ok) {
+                double Pm[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) Pm[k] = __ldg(P + (long long)view * 12 + k);
+                const int H = __ldg(img_hw + 2 * view), W = __ldg(img_hw + 2 * view + 1);
+                const uint8_t* __restrict__ img = images + __ldg(img_offset + view);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const Proj pr = project(Pm, cx, cy, voxel_coord(2 * t + e, rs, z0));
+                    const int32_t pw = round_to_i32(__ddiv_rn(pr.u, pr.q));
+                    const int32_t ph = round_to_i32(__ddiv_rn(pr.t, pr.q));
+                    if ((pw < W) && (ph < H) && (pw >= 0) && (ph >= 0)) {
+                        const uint8_t* px = img + ((long long)ph * W + pw) * 3;
+                        y[e][0] = (float)__ldg(px); y[e][1] = (float)__ldg(px + 1); y[e][2] = (float)__ldg(px + 2);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float m = mean6 ? __ldg(mean6 + 3 * side + c) : 0.f;
+                const float y0 = y[0][c] - m, y1 = y[1][c] - m;               // preprocess_augmentation (CVC.py:110-111)
+                float l = __shfl_up_sync(0xffffffffu, y1, 1), r = __shfl_down_sync(0xffffffffu, y0, 1);
+                l = first_t ? 0.f : l; r = last_t ? 0.f : r;
+                v[0][3 * side + c] = l - y1; v[1][3 * side + c] = y0 + y1; v[2][3 * side + c] = y1 - y0; v[3][3 * side + c] = y0 - r;
+            }
+        }
+        if (active) {
+            const long long pos = dh * TP + t;
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_pack(v[f][2 * e], v[f][2 * e + 1], hi[e], lo[e]);
+                __half* dst = out + (((n * 2) * 4 + f) * 2 + 0) * volw * 8 + pos * 8;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + 4LL * 2 * volw * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+}
+
+int cvc_wino_launch(const CvcSource& src, int pc0, int n, int S, __half* out_wino, cudaStream_t stream) {
+    const long long total = (long long)n * S * S * (S / 2);
+    if (!total) return SN_OK;
+    SN_CHECK_ARG(S == 16 || S == 32 || S == 64, "cvc_wino: unsupported cube size %d", S);
+    const int blocks = (int)std::min<long long>(cdiv(total, 256), 148 * 16);
+    cvc_wino_kernel<<<blocks, 256, 0, stream>>>(src.images, src.img_offset, src.img_hw, src.n_views, src.P, src.xyz, src.resol, src.views, src.n_vp,
+                                                src.mean6, pc0, S, total, out_wino);
+    SN_LAUNCHED();
+    return SN_OK;
 }
 
 int pack_wino_launch(const float* x, int n, int C, int S, __half* out_wino, cudaStream_t stream) {

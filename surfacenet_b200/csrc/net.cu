@@ -228,7 +228,8 @@ static int64_t fp32_floats_per_pc(int D) {
     return 32 * V * 2 + 32 * V2 + 80 * V2 * 2 + 16 * V2 + 80 * V4 + 160 * V4 * 2 + 300 * V4 * 2 + 16 * V4 + 64 * V + 100 * V * 2 + 64;
 }
 
-int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out, void* ws, int64_t ws_bytes, int mode, cudaStream_t st);  // conv_tc.cu
+int tc_forward(const Net& net, const float* X, int n_pc, int D, float* prob_out, void* ws, int64_t ws_bytes, int mode, cudaStream_t st,
+               const CvcSource* src);  // conv_tc.cu
 int64_t tc_workspace_bytes(const Net& net, int n_pc, int D, int mode);
 
 static int fp32_forward_chunk(const Net& net, const float* X, int n, int D, float* prob_out, float* ws, cudaStream_t st) {
@@ -287,7 +288,15 @@ extern "C" int64_t sn_net_workspace_bytes(const sn_net* h, int n_pair_cubes, int
 extern "C" int sn_net_forward(const sn_net* h, const float* X_dev, int n_cubes, int n_vp, int D, const float* w_dev,
                               float* fused_out_dev, float* unfused_out_dev, void* workspace_dev, int64_t workspace_bytes,
                               int mode, void* stream) {
-    SN_CHECK_ARG(h && X_dev && fused_out_dev, "sn_net_forward: NULL argument");
+    SN_CHECK_ARG(h && X_dev, "sn_net_forward: NULL argument");
+    return sn::net_forward(h, X_dev, nullptr, n_cubes, n_vp, D, w_dev, fused_out_dev, unfused_out_dev, workspace_dev, workspace_bytes, mode, stream);
+}
+
+// the network input is either the fp32 CVC tensor X_dev or, for the forwards tc_gathers_directly() names, the gather's arguments (src)
+int sn::net_forward(const sn_net* h, const float* X_dev, const CvcSource* src, int n_cubes, int n_vp, int D, const float* w_dev, float* fused_out_dev,
+                    float* unfused_out_dev, void* workspace_dev, int64_t workspace_bytes, int mode, void* stream) {
+    SN_CHECK_ARG(h && (X_dev || src) && fused_out_dev, "sn_net_forward: NULL argument");
+    SN_CHECK_ARG(!src || tc_gathers_directly(h->net, D, mode), "sn_net_forward: this mode / cube size needs the CVC tensor");
     SN_CHECK_ARG(n_cubes >= 0 && n_vp >= 1, "sn_net_forward: bad sizes (n_cubes=%d n_vp=%d)", n_cubes, n_vp);
     SN_CHECK_ARG(D >= 4 && D % 4 == 0, "sn_net_forward: cube side %d must be a multiple of 4 (two 2^3 poolings)", D);
     SN_CHECK_ARG(w_dev || n_vp == 1, "sn_net_forward: w is required when N_viewPairs4inference >= 2 (nets/SurfaceNet.py:343-347)");
@@ -313,7 +322,7 @@ extern "C" int sn_net_forward(const sn_net* h, const float* X_dev, int n_cubes, 
         }
     } else {
         void* ws = workspace_dev ? (char*)workspace_dev + ar.off : nullptr;
-        rc = tc_forward(h->net, X_dev, n_pc, D, prob, ws, workspace_bytes - ar.off, mode, st);
+        rc = tc_forward(h->net, X_dev, n_pc, D, prob, ws, workspace_bytes - ar.off, mode, st, src);
     }
     if (rc != SN_OK) return rc;
     if (n_vp == 1) {

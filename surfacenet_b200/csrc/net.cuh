@@ -49,6 +49,16 @@ struct Net {
     void* tc = nullptr;       // tensor-core side tables (conv_tc.cu), created lazily at sn_net_create
 };
 
+// Where the network input comes from when the caller does not need the fp32 CVC tensor X itself: the arguments of the CVC gather
+// (utils/CVC.py:56-111).  The Winograd forward then colours conv1_1's operand straight from the images (conv_wg.cu:cvc_wino_kernel)
+// and X (24 B per pair-voxel written + read back) is never materialised.
+struct CvcSource {
+    const uint8_t* images; const int64_t* img_offset; const int32_t* img_hw; int n_views;
+    const double* P; const float* xyz; const float* resol; const int32_t* views;     // views: (N_cubes, N_vp, 2) = 2 slots per pair-cube
+    int n_vp; const float* mean6;
+};
+bool tc_gathers_directly(const Net& net, int D, int mode);                           // conv_tc.cu: the forward of (D, mode) can take a CvcSource
+
 // per-launch CUDA-event timing of the conv units (sn_profile_enable / sn_profile_collect; bench.py roofline)
 void prof_begin(int unit, cudaStream_t st);
 void prof_end(int unit, cudaStream_t st);
@@ -62,3 +72,9 @@ int relimp_launch(const Net& net, const float* features, int64_t n_rows, int n_p
 }  // namespace sn
 
 struct sn_net { sn::Net net; };
+
+namespace sn {
+// net.cu: sn_net_forward's body; the input is X_dev or, for the forwards tc_gathers_directly() names, the gather's arguments
+int net_forward(const sn_net* h, const float* X_dev, const CvcSource* src, int n_cubes, int n_vp, int D, const float* w_dev, float* fused_out_dev,
+                float* unfused_out_dev, void* workspace_dev, int64_t workspace_bytes, int mode, void* stream);
+}

@@ -24,6 +24,15 @@ constexpr int32_t RP_EMPTY = -1;
 
 struct RpKey { long long w, h; int32_t d; };
 
+// tables are ALLOCATED for the worst case (every voxel selected, rp_capacity) but only the first rp_dyn_cap(selected count) slots of
+// each are cleared and probed: a power of two >= 2 x the cube's selected voxels (load factor <= 1/2 as before).  Capacity only changes
+// where a key lands, never the result (the three passes are order independent and exact).
+__device__ __forceinline__ uint32_t rp_dyn_cap(int cnt, uint32_t cap) {
+    uint32_t c = 256;
+    while (c < 2u * (uint32_t)cnt) c <<= 1;
+    return c < cap ? c : cap;
+}
+
 struct RpCube {
     double P[12];
     float x0, y0, z0, rs;
@@ -115,6 +124,37 @@ __device__ __forceinline__ unsigned long long rp_rank(float p, int32_t d) {
     return ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(0xFFFFFFFFu - ((uint32_t)d ^ 0x80000000u));
 }
 
+// one selected voxel n of (cube b, view slot bt) in pass PASS
+template <typename T, int PASS>
+__device__ __forceinline__ void rp_item(const T* __restrict__ pred, const RpCube& cube, int b, int64_t bt, int n, int mult, int vol, uint32_t cap, uint32_t mask,
+                                        int32_t* cell_claim, int32_t* cell_best, int32_t* pix_claim, unsigned long long* pix_val, uint8_t* votes) {
+    int32_t* cc = cell_claim + bt * cap;
+    int32_t* cb = cell_best + bt * cap;
+    const RpKey kn = cube.key(n);
+    if (PASS == 0) {
+        const uint32_t s = rp_probe<true, true>(cc, mask, cube, n, kn);
+        atomicMax(&cb[s], n);                                           // last write wins (:251)
+        return;
+    }
+    const uint32_t s = rp_probe<true, false>(cc, mask, cube, n, kn);
+    if (cb[s] != n) return;                                             // not the cell's representative
+    int32_t* pc = pix_claim + bt * cap;
+    unsigned long long* pv = pix_val + bt * cap;
+    const unsigned long long rank = rp_rank(rp_load<T>(pred, (int64_t)b * vol + n), kn.d);
+    if (PASS == 1) {
+        const uint32_t q = rp_probe<false, true>(pc, mask, cube, n, kn);
+        atomicMax(&pv[q], rank);                                        // argmax over depth (:253)
+    } else {
+        const uint32_t q = rp_probe<false, false>(pc, mask, cube, n, kn);
+        if (pv[q] == rank) {                                            // (:255-256) + multiplicity (:258)
+            const int64_t o = (int64_t)b * vol + n;
+            atomicAdd(reinterpret_cast<unsigned int*>(votes + (o & ~(int64_t)3)), (unsigned)mult << (8 * (int)(o & 3)));
+        }
+    }
+}
+
+// grid = (blocks per slot, cube x view slot): the blocks of a slot stride over the cube's SELECTED voxels (their number is only known on
+// the device; a grid sized for the whole volume would be mostly blocks that exit at once)
 template <typename T, int PASS>
 __global__ void __launch_bounds__(RP_THREADS)
 rp_pass_kernel(const T* __restrict__ pred, const int32_t* __restrict__ viewpairs, const double* __restrict__ P, int n_views,
@@ -129,39 +169,36 @@ rp_pass_kernel(const T* __restrict__ pred, const int32_t* __restrict__ viewpairs
     if ((int)(blockIdx.x * RP_THREADS) >= cnt) return;
     RpCube cube; int mult;
     if (!rp_setup(b, t, NT, n_views, viewpairs, P, xyz, resol, D, cube, mult)) return;
-    const int e = blockIdx.x * RP_THREADS + threadIdx.x;
-    if (e >= cnt) return;
-    const int n = sel_list[(int64_t)b * vol + e];
-    const uint32_t mask = cap - 1;
-    int32_t* cc = cell_claim + (int64_t)bt * cap;
-    int32_t* cb = cell_best + (int64_t)bt * cap;
-    const RpKey kn = cube.key(n);
-    if (PASS == 0) {
-        const uint32_t s = rp_probe<true, true>(cc, mask, cube, n, kn);
-        atomicMax(&cb[s], n);                                           // last write wins (:251)
-        return;
-    }
-    const uint32_t s = rp_probe<true, false>(cc, mask, cube, n, kn);
-    if (cb[s] != n) return;                                             // not the cell's representative
-    int32_t* pc = pix_claim + (int64_t)bt * cap;
-    unsigned long long* pv = pix_val + (int64_t)bt * cap;
-    const unsigned long long rank = rp_rank(rp_load<T>(pred, (int64_t)b * vol + n), kn.d);
-    if (PASS == 1) {
-        const uint32_t q = rp_probe<false, true>(pc, mask, cube, n, kn);
-        atomicMax(&pv[q], rank);                                        // argmax over depth (:253)
-    } else {
-        const uint32_t q = rp_probe<false, false>(pc, mask, cube, n, kn);
-        if (pv[q] == rank) {                                            // (:255-256) + multiplicity (:258)
-            const int64_t o = (int64_t)b * vol + n;
-            atomicAdd(reinterpret_cast<unsigned int*>(votes + (o & ~(int64_t)3)), (unsigned)mult << (8 * (int)(o & 3)));
-        }
-    }
+    const uint32_t mask = rp_dyn_cap(cnt, cap) - 1;
+    for (int e = blockIdx.x * RP_THREADS + threadIdx.x; e < cnt; e += gridDim.x * RP_THREADS)
+        rp_item<T, PASS>(pred, cube, b, bt, sel_list[(int64_t)b * vol + e], mult, vol, cap, mask, cell_claim, cell_best, pix_claim, pix_val, votes);
 }
 
 __global__ void cast_f32_f16_kernel(const float* __restrict__ in, int64_t n, __half* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);       // sparseCubes.py:115 astype(np.float16)
+}
+
+// claims = EMPTY, cell representatives = -1, pixel maxima = 0 over the slots the passes will use
+__global__ void __launch_bounds__(RP_THREADS)
+rp_clear_kernel(const int32_t* __restrict__ sel_count, int n_slots, uint32_t cap, int32_t* __restrict__ cell_claim,
+                int32_t* __restrict__ cell_best, int32_t* __restrict__ pix_claim, unsigned long long* __restrict__ pix_val) {
+    const int bt = blockIdx.y;
+    const int cnt = sel_count[bt / n_slots];
+    if (cnt == 0) return;
+    const uint32_t capb = rp_dyn_cap(cnt, cap);
+    const int64_t base = (int64_t)bt * cap;
+    // 4 slots per thread and step: 16-byte stores (cap and capb are multiples of 256, the tables 256-byte aligned)
+    const int4 m1 = make_int4(-1, -1, -1, -1);
+    const ulonglong2 z = make_ulonglong2(0ull, 0ull);
+    for (uint32_t i = (blockIdx.x * RP_THREADS + threadIdx.x) * 4; i < capb; i += gridDim.x * RP_THREADS * 4) {
+        *reinterpret_cast<int4*>(cell_claim + base + i) = m1;
+        *reinterpret_cast<int4*>(cell_best + base + i) = m1;
+        *reinterpret_cast<int4*>(pix_claim + base + i) = m1;
+        *reinterpret_cast<ulonglong2*>(pix_val + base + i) = z;
+        *reinterpret_cast<ulonglong2*>(pix_val + base + i + 2) = z;
+    }
 }
 
 uint32_t rp_capacity(int D) {
@@ -194,6 +231,7 @@ int sn::raypool_enqueue(const void* pred_dev, int pred_is_f16, int has_thresh, f
     SN_CHECK_ARG(pred_dev && viewpairs_dev && P_dev && xyz_dev && resol_dev && votes_out_dev, "sn_raypool_votes: NULL argument");
     SN_CHECK_ARG(n_cubes >= 0 && n_vp >= 1 && n_vp <= 127 && D >= 1 && D <= 256 && n_views >= 1, "sn_raypool_votes: bad sizes (n_cubes=%d n_vp=%d D=%d)", n_cubes, n_vp, D);
     if (n_cubes == 0) return SN_OK;
+    SN_CHECK_ARG(((uintptr_t)workspace_dev & 15) == 0, "sn_raypool_votes: the workspace must be 16-byte aligned");
     const int64_t need = sn_raypool_workspace_bytes(n_cubes, n_vp, D);
     if (!workspace_dev || workspace_bytes < need) { set_error("sn_raypool_votes: workspace %lld B < %lld B", (long long)workspace_bytes, (long long)need); return SN_ERR_NOMEM; }
     const int vol = D * D * D;
@@ -213,25 +251,30 @@ int sn::raypool_enqueue(const void* pred_dev, int pred_is_f16, int has_thresh, f
     if (flags_dev_out) *flags_dev_out = flags;
     // flags + sel_count are contiguous at the head of the arena
     SN_CUDA(cudaMemsetAsync(flags, 0, (char*)sel_list - (char*)flags, st));
-    SN_CUDA(cudaMemsetAsync(cell_claim, 0xFF, (char*)pix_val - (char*)cell_claim, st));   // claims = EMPTY, best = -1
-    SN_CUDA(cudaMemsetAsync(pix_val, 0, bt * cap * 8, st));
     SN_CUDA(cudaMemsetAsync(votes_acc, 0, align_up((int64_t)n_cubes * vol, 4), st));      // rayPooling.py:235
-    dim3 gsel((unsigned)cdiv(vol, RP_THREADS), (unsigned)n_cubes), gpass((unsigned)cdiv(vol, RP_THREADS), (unsigned)bt);
+    // >= 16 blocks per SM over all slots when the volume allows it; each slot's blocks loop over its selected voxels
+    const unsigned per_slot = (unsigned)std::min<int64_t>(cdiv(vol, RP_THREADS), std::max<int64_t>(8, cdiv(148 * 16, bt)));
+    dim3 gsel((unsigned)cdiv(vol, RP_THREADS), (unsigned)n_cubes), gpass(per_slot, (unsigned)bt);
+    dim3 gclr((unsigned)std::min<int64_t>(cdiv((int64_t)cap, RP_THREADS * 4), 32), (unsigned)bt);
+#define SN_RP_CLEAR rp_clear_kernel<<<gclr, RP_THREADS, 0, st>>>(sel_count, 2 * n_vp, cap, cell_claim, cell_best, pix_claim, pix_val); SN_LAUNCHED()
 #define SN_RP_ARGS viewpairs_dev, P_dev, n_views, xyz_dev, resol_dev, n_vp, D, vol, cap, sel_count, sel_list, cell_claim, cell_best, pix_claim, pix_val, votes_acc
     if (pred_is_f16) {
         const __half* p = (const __half*)pred_dev;
         rp_select_kernel<__half><<<gsel, RP_THREADS, 0, st>>>(p, has_thresh, thresh, vol, sel_count, sel_list, flags); SN_LAUNCHED();
+        SN_RP_CLEAR;
         rp_pass_kernel<__half, 0><<<gpass, RP_THREADS, 0, st>>>(p, SN_RP_ARGS); SN_LAUNCHED();
         rp_pass_kernel<__half, 1><<<gpass, RP_THREADS, 0, st>>>(p, SN_RP_ARGS); SN_LAUNCHED();
         rp_pass_kernel<__half, 2><<<gpass, RP_THREADS, 0, st>>>(p, SN_RP_ARGS); SN_LAUNCHED();
     } else {
         const float* p = (const float*)pred_dev;
         rp_select_kernel<float><<<gsel, RP_THREADS, 0, st>>>(p, has_thresh, thresh, vol, sel_count, sel_list, flags); SN_LAUNCHED();
+        SN_RP_CLEAR;
         rp_pass_kernel<float, 0><<<gpass, RP_THREADS, 0, st>>>(p, SN_RP_ARGS); SN_LAUNCHED();
         rp_pass_kernel<float, 1><<<gpass, RP_THREADS, 0, st>>>(p, SN_RP_ARGS); SN_LAUNCHED();
         rp_pass_kernel<float, 2><<<gpass, RP_THREADS, 0, st>>>(p, SN_RP_ARGS); SN_LAUNCHED();
     }
 #undef SN_RP_ARGS
+#undef SN_RP_CLEAR
     SN_CUDA(cudaMemcpyAsync(votes_out_dev, votes_acc, (int64_t)n_cubes * vol, cudaMemcpyDeviceToDevice, st));
     return SN_OK;
 }

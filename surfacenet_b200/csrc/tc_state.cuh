@@ -63,5 +63,7 @@ int raw_to_wino_launch(const __half* in_raw, int n, int cg_in_total, int cg_in_o
 
 // fp32 NCDHW input (n, C <= 8, S^3) -> group 0 of a 2-group Winograd-domain tensor (conv1_1's operand)
 int pack_wino_launch(const float* x, int n, int C, int S, __half* out_wino, cudaStream_t stream);
+// the same operand for pair-cubes [pc0, pc0 + n) coloured straight from the images: CVC gather + mean subtraction + input transform in one pass
+int cvc_wino_launch(const CvcSource& src, int pc0, int n, int S, __half* out_wino, cudaStream_t stream);
 
 }  // namespace sn

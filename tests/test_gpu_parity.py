@@ -519,6 +519,52 @@ def test_infer_batch_device_equals_host_entry(torch_cuda, params, cams):
     assert empty["fused"].shape == (0, 1, D, D, D)
 
 
+@pytest.mark.parametrize("D,n_cubes,n_vp", [(64, 1, 2), (32, 3, 3), (16, 2, 1)])
+def test_fused_gather_is_bit_identical_to_cvc_then_forward(torch_cuda, params, cams, D, n_cubes, n_vp):
+    """infer_batch colours conv1_1's Winograd operand straight from the images (conv_wg.cu:cvc_wino_kernel); the documented
+    two-step form -- CVC.gen_coloredCubes + preprocess_augmentation, then nViewPair_SurfaceNet_fn(X, w) -- must give the SAME bits,
+    also for voxels outside the image (one cube is placed so that part of it projects out of the frame)."""
+    import torch
+    from surfacenet_b200 import CVC, SurfaceNet, pipeline
+    from surfacenet_b200.device import DeviceScene
+    _, pairs, xyz, resol, imgs = _real_like_X(cams, 4, n_cubes=n_cubes, n_vp=n_vp, seed=21 + D)
+    xyz[-1] = np.array([-160.0, 95.0, 640.0], np.float32)                 # partly outside the 1600 x 1200 frame of most views
+    w = (np.random.RandomState(D).rand(n_cubes, n_vp) + 0.1).astype(np.float32)
+    net = SurfaceNet.Net(params)
+    hp = pipeline.HotPath(net, DeviceScene(cams, imgs))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    got = hp.infer_batch(dev(pairs.astype(np.int32)), dev(xyz), dev(resol), dev(w) if n_vp > 1 else None, D, want_unfused=True, ray_pool=False)
+    X = CVC.gen_coloredCubes(pairs, xyz, resol, cams, imgs, D)
+    _, X = CVC.preprocess_augmentation(None, X, mean_rgb=util.MEAN6[None, :, None, None, None], augment_ON=False, crop_ON=False)
+    scope = (X != -util.MEAN6[None, :, None, None, None]).mean()
+    assert 0.05 < scope < 0.999, scope                                     # both in-image and out-of-image voxels are present
+    fused, unf = net.forward(dev(X), dev(w) if n_vp > 1 else None, n_vp)
+    assert np.array_equal(got["fused"].cpu().numpy(), fused.cpu().numpy())
+    if n_vp > 1:
+        assert np.array_equal(got["unfused"].cpu().numpy(), unf.cpu().numpy())
+
+
+def test_raypool_dense_selection_uses_full_tables(torch_cuda, cams):
+    """Ray-pool hash tables are sized by the cube's selected-voxel count (rp_dyn_cap): every voxel selected drives them to the
+    allocated worst case, a handful keeps the 256-slot minimum; both against the oracle, in one batched call."""
+    from oracle import raypool_oracle
+    from surfacenet_b200 import rayPooling
+    D = 32
+    rs = np.random.RandomState(12)
+    pred = np.stack([(rs.rand(D, D, D) * 0.5 + 0.47).astype(np.float16),                     # all selected
+                     np.where(rs.rand(D, D, D) > 0.9995, 0.9, 0.1).astype(np.float16)])      # ~16 voxels selected
+    pairs = np.array([[[3, 4], [4, 9]], [[22, 23], [30, 3]]], np.int32)
+    xyz = np.array([[5.0, -20.0, 640.0], [-14.0, 12.0, 655.0]], np.float32)
+    resol = np.full(2, 0.4, np.float32)
+    import torch
+    votes = rayPooling.votes_device(torch.from_numpy(pred).cuda(), torch.from_numpy(pairs).cuda(), torch.from_numpy(xyz).cuda(),
+                                    torch.from_numpy(resol).cuda(), torch.from_numpy(cams).cuda(), cams.shape[0], 0.46).cpu().numpy()
+    for b in range(2):
+        ref = raypool_oracle.rayPooling_1cube_numpy(cams, None, pred[b], pairs[b], xyz[b], resol[b], prediction_thresh=0.46)
+        assert np.array_equal(votes[b], ref.astype(np.uint8))
+    assert votes[0].max() >= 1 and (pred[1] > 0.46).sum() < 128
+
+
 # ---- "next" rows N1 / N2: colour fusion and dense -> sparse ------------------------------------------------
 def test_color_fusion_matches_reference_outputs(torch_cuda, golden):
     from surfacenet_b200 import utils as sn_utils
@@ -663,3 +709,32 @@ def test_forward_with_fused_side_epilogue_subprocess(torch_cuda):
     assert out.returncode == 0, out.stderr[-2000:]
     e = [float(x) for x in out.stdout.strip().splitlines()[-1].split()[1:]]
     assert max(e) <= PROB_TOL, e
+
+
+def test_fused_passes_are_bit_identical_to_the_separate_ones(torch_cuda, params, cams, tmp_path):
+    """The default chain (images -> conv1_1's operand in one pass; side_op1 + pool1 in one pass over conv1_3's output) against the
+    separate passes it replaces (SN_CVC_FUSED=0 SN_SIDE_POOL=0: cvc_gather + pack_wino, side_wino + pool_blk), in a child process
+    because the switches are read once: probabilities, float16 predictions and votes must be the SAME bits, 64^3 and 32^3."""
+    import os, subprocess, sys
+    body = ("import sys; sys.path.insert(0, %r)\n"
+            "import numpy as np, torch\n"
+            "from surfacenet_b200 import SurfaceNet, pipeline, weights\n"
+            "from surfacenet_b200.device import DeviceScene\n"
+            "from tests import util\n"
+            "from tests.test_gpu_parity import _real_like_X\n"
+            "cams = util.dtu_cameras(); hp = None\n"
+            "for D, nc, nv in ((64, 2, 2), (32, 3, 3)):\n"
+            "    _, pairs, xyz, resol, imgs = _real_like_X(cams, 4, n_cubes=nc, n_vp=nv, seed=40 + D)\n"
+            "    w = (np.random.RandomState(D).rand(nc, nv) + 0.1).astype(np.float32)\n"
+            "    hp = hp or pipeline.HotPath(SurfaceNet.Net(weights.synthetic_params(0)), DeviceScene(cams, imgs))\n"
+            "    o = hp.infer_batch_host(pairs, xyz, resol, w, D)\n"
+            "    np.savez(sys.argv[1] + '_%%d.npz' %% D, fused=o['fused'], pred16=o['pred16'], votes=o['votes'])\n" % util.REPO)
+    for tag, env in (("fused", {}), ("separate", {"SN_CVC_FUSED": "0", "SN_SIDE_POOL": "0"})):
+        out = subprocess.run([sys.executable, "-c", body, str(tmp_path / tag)], env=dict(os.environ, **env), stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-2000:]
+    for D in (64, 32):
+        a, b = np.load(str(tmp_path / ("fused_%d.npz" % D))), np.load(str(tmp_path / ("separate_%d.npz" % D)))
+        for k in ("fused", "pred16", "votes"):
+            assert np.array_equal(a[k], b[k]), (D, k)
+        assert a["votes"].max() >= 1 and 0.02 < (a["fused"] > 0.46).mean() < 0.98

@@ -7,7 +7,7 @@ model files default to the reference's paths below `input_data_rootFld` (they ar
 normally pass parameter lists or their own files)."""
 import os
 import numpy as np
-from . import camera, image, reconstruct, similarityNet, weights
+from . import camera, image, reconstruct, similarityNet, sparseCubes, weights
 
 PRETRAINED_SURFACENET = 'SurfaceNet_models/2D_2_3D-19-0.918_0.951.model'          # params.py:106
 PRETRAINED_SIMILNET = 'SurfaceNet_models/epoch33_acc_tr0.707_val0.791.model'      # params.py:92
@@ -18,9 +18,9 @@ def reconstruction(datasetFolder, model, imgNamePattern, poseNamePattern, initia
                    mode="exact", weighted_fusion=True, batch_size=16, min_prob=0.46, tau=0.7, gamma=0.8, cube_overlapping_ratio=0.5,
                    rank=0, world_size=1):
     """-> path of the saved NPZ ('model{model}-{N_views}views.npz' in outputFolder, main_reconstruct.py:180-183) or "Empty!"."""
-    if initialPtsNamePattern is not None:
-        raise NotImplementedError("initial point clouds are read from PLY files (scene.readPointCloud_xyz); build the cubes with "
-                                  "reconstruct.quantize_pts_to_cubes and call reconstruct.reconstruct_cubes instead")
+    initial_pts_xyz = None
+    if initialPtsNamePattern is not None:                                                                                                # :57
+        initial_pts_xyz = sparseCubes.readPointCloud_xyz(os.path.join(datasetFolder, initialPtsNamePattern))
     images_list = image.readImages(datasetFolder=datasetFolder, imgNamePattern=imgNamePattern, viewList=viewList, return_list=True)      # :48
     cameraPOs_np = camera.readCameraPOs_as_np(datasetFolder=datasetFolder, datasetName=datasetName, poseNamePattern=poseNamePattern,
                                               model=model, viewList=viewList)                                                         # :49
@@ -34,5 +34,6 @@ def reconstruction(datasetFolder, model, imgNamePattern, poseNamePattern, initia
     out = reconstruct.reconstruction(images_list, cameraPOs_np, np.asarray(BB, dtype=np.float64), resol, N_viewPairs4inference, sp, mp,
                                      outputFolder=outputFolder, cube_D=cube_D, mode=mode, weighted_fusion=weighted_fusion,
                                      batch_size=batch_size, min_prob=min_prob, tau=tau, gamma=gamma,
-                                     cube_overlapping_ratio=cube_overlapping_ratio, model=model, rank=rank, world_size=world_size)
+                                     cube_overlapping_ratio=cube_overlapping_ratio, model=model, rank=rank, world_size=world_size,
+                                     initial_pts_xyz=initial_pts_xyz)
     return out if out == "Empty!" else out["npz_path"]

@@ -128,11 +128,13 @@ def finish(result, npz_path=None, ply_path=None, tau=TAU, gamma=GAMMA, cube_D=64
 def reconstruction(images_list, cameraPOs_np, BB, resol, N_viewPairs4inference, surfacenet_params, similnet_params, outputFolder=None,
                    cube_D=64, mode="exact", weighted_fusion=True, batch_size=16, min_prob=MIN_PROB, tau=TAU, gamma=GAMMA,
                    cube_overlapping_ratio=0.5, patchSize=64, batchSize_patch2embedding=1024, batchSize_pair=1 << 20, model="model",
-                   rank=0, world_size=1, group=None):
+                   rank=0, world_size=1, group=None, initial_pts_xyz=None):
     """main_reconstruct.reconstruction (main_reconstruct.py:28-183) from in-memory inputs (the reference reads `images_list`,
     `cameraPOs_np` and BB from files at :49-50 and params.load_modelSpecific_params): cube grid -> early rejection (similarityNet patch
     embeddings, pair dissimilarity) -> view-pair selection -> SurfaceNet inference on the fused sparse path -> fixed-threshold mask,
     cross-cube denoising, PLY + NPZ.  Every stage runs on the GPU drop-ins of this package.
+    initial_pts_xyz (N, 3): the cubes cover this point cloud (scene.quantizePts2Cubes, main_reconstruct.py:57-60) instead of the whole
+    bounding box; with an outputFolder the cube centres are written to 'initialCubes.ply' as at main_reconstruct.py:61.
     world_size > 1 (one process per GPU, torch.distributed initialised): the cube batches are dealt to the ranks, the sparse lists are
     gathered so that every rank holds the whole scene before the cross-cube stages, and ONLY rank 0 writes the PLY / NPZ files.
     -> "Empty!" or dict(npz_path, ply_path, result=(the seven sparse-list items), vxl_mask_list, vxl_maskDenoised_list, validCubes,
@@ -146,7 +148,12 @@ def reconstruction(images_list, cameraPOs_np, BB, resol, N_viewPairs4inference, 
     Dc = CUBE_DCENTER.get(int(cube_D), int(cube_D))
     cameraPOs_np = np.asarray(cameraPOs_np, dtype=np.float64)
     cameraTs_np = camera.cameraPs2Ts(cameraPOs_np)                                                        # :51
-    cubes_param_np, cube_D_mm = initialize_cubes(resol, cube_D, Dc, cube_overlapping_ratio, BB)            # :53-55
+    if initial_pts_xyz is None:
+        cubes_param_np, cube_D_mm = initialize_cubes(resol, cube_D, Dc, cube_overlapping_ratio, BB)        # :53-55
+    else:
+        cubes_param_np, cube_D_mm = quantize_pts_to_cubes(initial_pts_xyz, resol, cube_D, Dc, cube_overlapping_ratio, BB)   # :57-60
+    if outputFolder is not None and rank == 0:
+        sparseCubes.save2ply(os.path.join(outputFolder, 'initialCubes.ply'), xyz_np=cubes_param_np['xyz'] + cube_D_mm / 2)    # :61
     img_h_corner, img_w_corner = camera.perspectiveProj_cubesCorner(cameraPOs_np, cubes_param_np['xyz'], cube_D_mm, return_int_hw=False)
     centers = cubes_param_np['xyz'] + cube_D_mm / 2
     img_h_center, img_w_center = camera.perspectiveProj(cameraPOs_np, centers, return_int_hw=False)        # :63-65

@@ -151,6 +151,55 @@ def save2ply(ply_filePath, xyz_np, rgb_np=None, normal_np=None):
     return 1
 
 
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2", "ushort": "u2", "uint16": "u2",
+              "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+
+def readPointCloud_xyz(pointCloudFile):
+    """utils/scene.py:111-114 (PlyData.read(file)['vertex'] x / y / z -> (N, 3)) without plyfile: the vertex element of an
+    ascii / binary_little_endian / binary_big_endian PLY whose properties are scalars, as the initial point clouds of
+    main_reconstruct.py:57 are.  The columns keep the file's dtype, as np.c_ of the plyfile columns does."""
+    with open(pointCloudFile, "rb") as f:
+        raw = f.read()
+    end = raw.find(b"end_header")
+    if not raw.startswith(b"ply") or end < 0:
+        raise ValueError("{} is not a PLY file".format(pointCloudFile))
+    end = raw.index(b"\n", end) + 1
+    fmt, n_vertex, props, element, before = None, 0, [], None, 0
+    for line in raw[:end].decode("ascii", "replace").splitlines():
+        tok = line.split()
+        if not tok:
+            continue
+        if tok[0] == "format":
+            fmt = tok[1]
+        elif tok[0] == "element":
+            element = tok[1]
+            if element == "vertex":
+                n_vertex = int(tok[2])
+            elif not props:
+                before += int(tok[2])
+        elif tok[0] == "property" and element == "vertex":
+            if tok[1] == "list":
+                raise ValueError("list properties in the vertex element are not supported ({})".format(pointCloudFile))
+            props.append((tok[2], _PLY_TYPES[tok[1]]))
+    if before:
+        raise ValueError("elements before 'vertex' are not supported ({})".format(pointCloudFile))
+    names = [n for n, _ in props]
+    if not all(a in names for a in "xyz"):
+        raise ValueError("the vertex element of {} has no x / y / z".format(pointCloudFile))
+    if fmt == "ascii":
+        rows = raw[end:].decode("ascii").split("\n")[:n_vertex]
+        table = np.array([r.split()[:len(props)] for r in rows], dtype=np.float64).reshape(n_vertex, len(props))
+        cols = [table[:, names.index(a)].astype(props[names.index(a)][1]) for a in "xyz"]
+    else:
+        order = {"binary_little_endian": "<", "binary_big_endian": ">"}.get(fmt)
+        if order is None:
+            raise ValueError("unknown PLY format {!r} ({})".format(fmt, pointCloudFile))
+        v = np.frombuffer(raw[end:], dtype=np.dtype([(n, order + t) for n, t in props]), count=n_vertex)
+        cols = [v[a].astype(v[a].dtype.newbyteorder("=")) for a in "xyz"]
+    return np.c_[cols[0], cols[1], cols[2]]
+
+
 def save_sparseCubes_2ply(vxl_mask_list, vxl_ijk_list, rgb_list, param, ply_filePath, normal_list=None):
     """utils/sparseCubes.py:287-327: voxel xyz = ijk * resol + cube xyz (float32) of the masked voxels -> PLY."""
     vxl_mask_np = np.concatenate([np.asarray(m).astype(bool) for m in vxl_mask_list], axis=0)

@@ -226,3 +226,13 @@ def test_main_reconstruct_dropin_from_files(tmp_path, cams):
     assert npz.endswith("model9-4views.npz") and os.path.exists(npz)
     back = sparseCubes.load_sparseCubes(npz)
     assert len(back[0]) > 0 and back[6].shape[1:] == (2, 2) and os.path.exists(str(tmp_path / "out" / "fixThresh_tau0.5_gamma0.0.ply"))
+    grid_xyz, _ = util.read_ply(str(tmp_path / "out" / "initialCubes.ply"))                     # main_reconstruct.py:61
+    # the same scene from an initial point cloud (main_reconstruct.py:57-60): the cubes cover the points only
+    pts = grid_xyz[::7][:3].astype(np.float32)
+    sparseCubes.save2ply(str(tmp_path / "init_pts.ply"), pts)
+    npz2 = main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#_3.png", "cal/pos_#.txt", "init_pts.ply", str(tmp_path / "out2"), 2, np.float32(0.4),
+                                           np.array([[-10.0, 15.0], [-20.0, 5.0], [620.0, 645.0]]), views, surfacenet_model=weights.synthetic_params(0),
+                                           similnet_model=sp, cube_D=32, tau=0.5, gamma=0.0)
+    cubes2, _ = util.read_ply(str(tmp_path / "out2" / "initialCubes.ply"))
+    assert 8 <= cubes2.shape[0] <= 24 and cubes2.shape[0] < grid_xyz.shape[0]                  # 2^3 cells per point, shared cells counted once
+    assert npz2 == "Empty!" or len(sparseCubes.load_sparseCubes(npz2)[0]) <= cubes2.shape[0]

@@ -472,3 +472,43 @@ def test_initialize_cubes_float32_resol_uses_float64_arithmetic():
     q32, _ = reconstruct.quantize_pts_to_cubes(pts, np.float32(0.4), 64, 52, 0.5)
     q64, _ = reconstruct.quantize_pts_to_cubes(pts, r, 64, 52, 0.5)
     assert np.array_equal(q32["xyz"], q64["xyz"]) and np.array_equal(q32["ijk"], q64["ijk"])
+
+
+def test_readPointCloud_xyz_formats(tmp_path):
+    """utils/scene.py:111-114 without plyfile: the x / y / z columns of the vertex element, binary (both byte orders, extra properties
+    such as normals / colours in between) and ascii; the file's dtype is kept, as np.c_ of the plyfile columns does."""
+    from surfacenet_b200 import sparseCubes
+    rs = np.random.RandomState(2)
+    xyz = (rs.rand(37, 3) * 100 - 50).astype(np.float32)
+    rgb = rs.randint(0, 256, size=(37, 3)).astype(np.uint8)
+    nrm = rs.randn(37, 3).astype(np.float32)
+    p = str(tmp_path / "a.ply")
+    sparseCubes.save2ply(p, xyz, rgb_np=rgb, normal_np=nrm)                               # x y z nx ny nz red green blue, little endian
+    got = sparseCubes.readPointCloud_xyz(p)
+    assert got.dtype == np.float32 and np.array_equal(got, xyz)
+    # big endian, double coordinates, a face element after the vertices
+    dt = np.dtype([("x", ">f8"), ("red", "u1"), ("y", ">f8"), ("z", ">f8")])
+    v = np.zeros(5, dt); v["x"], v["y"], v["z"], v["red"] = xyz[:5, 0], xyz[:5, 1], xyz[:5, 2], 7
+    hdr = ("ply\nformat binary_big_endian 1.0\ncomment made by hand\nelement vertex 5\nproperty double x\nproperty uchar red\n"
+           "property double y\nproperty double z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n")
+    with open(str(tmp_path / "b.ply"), "wb") as f:
+        f.write(hdr.encode("ascii")); f.write(v.tobytes()); f.write(bytes([3]) + np.array([0, 1, 2], ">i4").tobytes())
+    got = sparseCubes.readPointCloud_xyz(str(tmp_path / "b.ply"))
+    assert got.dtype == np.float64 and np.array_equal(got, xyz[:5].astype(np.float64))
+    with open(str(tmp_path / "c.ply"), "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nproperty uchar red\nend_header\n")
+        for r in xyz[:3]:
+            f.write("%r %r %r 9\n" % (float(r[0]), float(r[1]), float(r[2])))
+    got = sparseCubes.readPointCloud_xyz(str(tmp_path / "c.ply"))
+    assert got.dtype == np.float32 and np.array_equal(got, xyz[:3])
+    with open(str(tmp_path / "d.ply"), "wb") as f:
+        f.write(b"not a ply")
+    with pytest.raises(ValueError):
+        sparseCubes.readPointCloud_xyz(str(tmp_path / "d.ply"))
+    # the cubes of a point cloud read back from a file equal the cubes of the array (main_reconstruct.py:57-60)
+    from surfacenet_b200 import reconstruct
+    pts = np.array([[10.0, -5.0, 620.0], [10.3, -5.2, 620.1], [25.0, 3.0, 640.0]], np.float32)
+    sparseCubes.save2ply(str(tmp_path / "pts.ply"), pts)
+    a, _ = reconstruct.quantize_pts_to_cubes(sparseCubes.readPointCloud_xyz(str(tmp_path / "pts.ply")), np.float32(0.4), 32, 26, 0.5)
+    b, _ = reconstruct.quantize_pts_to_cubes(pts, np.float32(0.4), 32, 26, 0.5)
+    assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["ijk"], b["ijk"])

@@ -403,7 +403,7 @@ def test_main_reconstruct_dropin_reads_inputs_then_needs_gpu(tmp_path):
         main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#.png", "cal/pos_#.txt", None, str(tmp_path / "out"), 1, np.float32(0.4),
                                         np.array([[0., 10.], [0., 10.], [600., 610.]]), [1, 2], surfacenet_model=weights.synthetic_params(0),
                                         similnet_model=similarityNet.synthetic_params(0), cube_D=32)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(FileNotFoundError):                       # an initial point cloud (main_reconstruct.py:57) is read before anything else
         main_reconstruct.reconstruction(str(tmp_path), 9, "rect_#.png", "cal/pos_#.txt", "pts.ply", str(tmp_path / "out"), 1, np.float32(0.4),
                                         np.zeros((3, 2)), [1, 2])
 

@@ -234,5 +234,5 @@ def test_main_reconstruct_dropin_from_files(tmp_path, cams):
                                            np.array([[-10.0, 15.0], [-20.0, 5.0], [620.0, 645.0]]), views, surfacenet_model=weights.synthetic_params(0),
                                            similnet_model=sp, cube_D=32, tau=0.5, gamma=0.0)
     cubes2, _ = util.read_ply(str(tmp_path / "out2" / "initialCubes.ply"))
-    assert 8 <= cubes2.shape[0] <= 24 and cubes2.shape[0] < grid_xyz.shape[0]                  # 2^3 cells per point, shared cells counted once
+    assert 2 <= cubes2.shape[0] <= 6 and cubes2.shape[0] < grid_xyz.shape[0]                   # cells floor and floor + 1 per point (scene.py:92-98), shared cells once
     assert npz2 == "Empty!" or len(sparseCubes.load_sparseCubes(npz2)[0]) <= cubes2.shape[0]

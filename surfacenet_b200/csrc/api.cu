@@ -1,5 +1,6 @@
 // The per-batch hot loop of main_reconstruct.py:132-162 as one device-resident call.
 #include "net.cuh"
+#include <mutex>
 
 using namespace sn;
 
@@ -86,6 +87,8 @@ extern "C" int sn_infer_batch(const sn_net* h, const uint8_t* images_dev, const 
 struct HostCopyLane { cudaStream_t st = nullptr; cudaEvent_t ready = nullptr, done = nullptr; };
 static int host_copy_lane(HostCopyLane** out) {
     static HostCopyLane lanes[64];
+    static std::mutex mu;                                   // first use may come from several host threads (ctypes releases the GIL)
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     SN_CUDA(cudaGetDevice(&dev));
     SN_CHECK_ARG(dev >= 0 && dev < 64, "sn_infer_batch_host: device ordinal %d", dev);

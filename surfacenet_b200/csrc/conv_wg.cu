@@ -57,7 +57,8 @@ struct ConvWgParams {
     int NA, NB;                     // A ring stages, weight ring slots (3 taps per slot)
     int hs, d_step;                 // hs: S = 8 geometry (below); d_step: d-planes per tile (AD, or 4 in the hs geometry)
     int d_fastest;                  // tile order (SN_WG_ORDER): 1 = d fastest, 0 = h fastest
-    int dbg;                        // SN_WG_DEBUG (timing experiments only): 1 = no output stores, 2 = no output math after the drains
+    int dbg;                        // SN_WG_DEBUG (timing experiments only, bit mask): 1 = no output stores, 2 = no output math after the drains,
+                                    // 4 = no weight traffic (64 B per ring slot), 8 = no lo-plane operand traffic -- the MMAs then read stale shared memory
     int a_prec_bytes;               // bytes of one precision plane of one A stage = 2 groups * HD*HH*TP*16
     long long n_tiles;              // tiles_h * tiles_d * n_pc * n_ntiles; every tile = 4 frequency passes
     int tiles_h, tiles_d, n_ntiles;
@@ -99,9 +100,16 @@ __device__ __forceinline__ WgTile wg_tile(const ConvWgParams& p, uint32_t t, int
 // warp -- both products of the split for all planes (AD = 1) or for the planes a % 2 == warp - 18 (AD >= 2) -- so the accumulation order
 // is fixed and the results are bit-reproducible.  SN_WG_ISSUERS=2 (compile time) splits the A_hi / A_lo products over the two warps with a
 // token handed back and forth per slot (tok[]): 3.4 % faster, NOT reproducible (see WG_NI above).
-template <int AD, int N, int OUT, bool HS, bool PAIR>
+// CL = CTAs per cluster sharing ONE weight stream (opt-in, SN_WG_CLUSTER=2): every CTA fetches 1/CL of each weight ring slot and multicasts it to all
+// of them (the CTAs of a cluster walk tiles with the same N tile in lockstep; slot releases are multicast commits), so the weights are requested from
+// L2 once per cluster instead of once per CTA.  Bit-identical results; MEASURED SLOWER at CL = 2 (C3 step 64.6 / 64.9 ms vs 61.7 / 62.4 ms interleaved
+// on one box, merge_conv2 19.4 - 20.0 vs 18.1 - 18.3 ms): every SM still ingests the full weight stream, pairs of CTAs now wait for each other, and
+// at cluster sizes <= 4 the L2 already merges neighbouring unicast requests (B300_MICROARCH.md, TMA multicast).  Default: CL = 1.
+template <int AD, int N, int OUT, bool HS, bool PAIR, int CL>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p) {
+    static_assert(CL == 1 || !HS, "the weight multicast is built for the full-row geometry");
+    constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
     constexpr int TPS = 3;                                             // taps per weight slot: the three kh taps of one kd
     // MMA issuers: SPLIT_PROD (SN_WG_ISSUERS=2, not bit-reproducible) = warp 18 the A_hi products, warp 19 the A_lo products; otherwise every
     // accumulator has ONE issuer: a single warp when AD = 1, two warps owning the even / odd d-planes when AD >= 2 (conv1_x)
@@ -133,7 +141,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], NI); }
-        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI); }
+        for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], NI * CL); }   // a slot is free when EVERY CTA of the cluster has consumed it
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], NI); mbar_init(&acc_empty[i], 512); }
         mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);            // the issue-order tokens
         // the hi issuer owns the token at the start: phase 0 of its barrier is completed here
@@ -149,6 +157,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
     if (OUT == WG_OUT_FINAL) for (int i = threadIdx.x; i < 128; i += WG_THREADS) w3_s[i] = (i < p.c_pad) ? p.w3[i] : 0.f;
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                               // the peers' barriers are initialised before anything remote can reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (warp >= 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG_CTRL_REGS));
@@ -166,10 +175,10 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                     for (int kh = 0; kh < n_sh; ++kh) {
                         mbar_wait(&a_empty[s], ph ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(&a_full[s], a_stage_bytes);
+                            const int n_pr = (p.dbg & 8) ? 1 : 2;                 // timing experiment: only the hi plane crosses L2 -> SM
+                            mbar_expect_tx(&a_full[s], (uint32_t)p.a_prec_bytes * n_pr);
                             const int h_lo = HS ? (kh - 1) * pad : c.h0 - pad;
-#pragma unroll
-                            for (int pr = 0; pr < 2; ++pr)
+                            for (int pr = 0; pr < n_pr; ++pr)
                                 tma_load_4d(smA + (size_t)s * a_stage_bytes + (size_t)pr * p.a_prec_bytes, &in_map, &a_full[s],
                                             0, h_lo, c.d0 - pad, ((c.pc * 2 + pr) * 4 + f) * p.cg_in + 2 * cb);
                         }
@@ -180,6 +189,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
     } else if (warp == 17) {
         // ===== B producer: the (frequency, channel block, tap) weight stages, TPS per ring slot =====
         const int total = p.stages_per_f / TPS;
+        const uint32_t cl_rank = (CL > 1) ? cluster_ctarank() : 0u;
         int s = 0; uint32_t ph = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const WgTile c = wg_tile(p, t, AD);
@@ -189,8 +199,15 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                 for (int it = 0; it < total; ++it) {
                     mbar_wait(&b_empty[s], ph ^ 1);
                     if (elect_one()) {
+                        if (p.dbg & 4) {                                        // timing experiment: (almost) no weight bytes cross L2 -> SM
+                            mbar_expect_tx(&b_full[s], 64);
+                            bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * slot_bytes, 64, &b_full[s]);
+                        } else {
                         mbar_expect_tx(&b_full[s], slot_bytes);
-                        if (!HS) {
+                        if (CL > 1) {                                       // my 1/CL of the slot, to every CTA of the cluster
+                            const uint32_t part = slot_bytes / CL;
+                            bulk_load_mc(smB + (size_t)s * b_slot_bytes + cl_rank * part, wsrc + (size_t)it * slot_bytes + cl_rank * part, part, &b_full[s], cl_mask);
+                        } else if (!HS) {
                             bulk_load(smB + (size_t)s * b_slot_bytes, wsrc + (size_t)it * slot_bytes, slot_bytes, &b_full[s]);
                         } else {                                            // slot = the three kd taps of (block it / 3, kh = it % 3): stages kd*3 + kh
                             const uint32_t stage_bytes = slot_bytes / TPS;
@@ -198,6 +215,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                             for (int kd = 0; kd < 3; ++kd)
                                 bulk_load(smB + (size_t)s * b_slot_bytes + (size_t)kd * stage_bytes, wsrc + (size_t)(cb * 9 + kd * 3 + kh) * stage_bytes,
                                           stage_bytes, &b_full[s]);
+                        }
                         }
                     }
                     __syncwarp();
@@ -210,12 +228,14 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
         const int me = warp - 18;
         const uint32_t ab_hi32 = 8u | (1u << 14);                            // SBO = 128 B (rows are 16 B apart, linearly), descriptor version 1
         const uint32_t a_lbo = (uint32_t)(p.a_prec_bytes >> 5) << 16;        // the second channel group of the stage
-        const uint32_t smB16 = smem_u32(smB) >> 4;
+        // descriptor start addresses are 14-bit CTA-relative fields (bytes >> 4): in a cluster launch the shared-window address of a CTA of rank > 0
+        // carries the rank above bit 24 and, unmasked, would spill into the LBO field next to it
+        const uint32_t smB16 = (smem_u32(smB) >> 4) & 0x3FFFu;
         const uint32_t a_stage16 = a_stage_bytes >> 4;
         const uint32_t b_slot16 = b_slot_bytes >> 4;
         const uint32_t plane16 = (uint32_t)(p.HH * p.TP);
         const uint32_t kd_step = plane16 * (uint32_t)p.dil, kh_step = (uint32_t)(p.TP * p.dil);
-        const uint32_t smA16 = (smem_u32(smA) >> 4) + ((SPLIT_PROD && me) ? ((uint32_t)p.a_prec_bytes >> 4) : 0u);   // product split: the lo issuer reads the lo precision plane
+        const uint32_t smA16 = ((smem_u32(smA) >> 4) & 0x3FFFu) + ((SPLIT_PROD && me) ? ((uint32_t)p.a_prec_bytes >> 4) : 0u);   // product split: the lo issuer reads the lo precision plane
         if (PAIR) {                                                   // virtual tap v -> taps (2v, 2v+1) of the 9; beyond, the weights are zero
             if (lane < 6) {
                 const int ta = min(2 * lane, 8), tb = min(2 * lane + 1, 8);
@@ -284,7 +304,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
                                 acc_flag = 1u;
                             }
                             if (SPLIT_PROD) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tok[me])) : "memory");   // pass the token
-                            tc_commit(&b_empty[sb]);
+                            if (CL > 1) tc_commit_mc(&b_empty[sb], cl_mask); else tc_commit(&b_empty[sb]);
                         }
                         __syncwarp();
                         acc_flag = 1u;
@@ -488,6 +508,7 @@ conv_wg_kernel(const __grid_constant__ CUtensorMap in_map, const ConvWgParams p)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                               // no CTA leaves while a peer may still write its shared memory / barriers
     if (warp == 19) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -836,15 +857,45 @@ static WgCfg wg_config(int S, int N, int dil) {
     return c;
 }
 
-template <int AD, int N, int OUT, bool HS, bool PAIR>
-static int wg_launch_t(const CUtensorMap& map, const ConvWgParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+template <int AD, int N, int OUT, bool HS, bool PAIR, int CL>
+static int wg_launch_c(const CUtensorMap& map, const ConvWgParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, N, OUT, HS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
+        SN_CUDA((cudaFuncSetAttribute(conv_wg_kernel<AD, N, OUT, HS, PAIR, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)));
         attr_set = true;
     }
-    conv_wg_kernel<AD, N, OUT, HS, PAIR><<<grid, WG_THREADS, smem, stream>>>(map, p);
+    if (CL == 1) {
+        conv_wg_kernel<AD, N, OUT, HS, PAIR, CL><<<grid, WG_THREADS, smem, stream>>>(map, p);
+        return SN_OK;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(WG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // persistent kernel: the whole grid must be resident at once, also as clusters (asked once per instance)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_wg_kernel<AD, N, OUT, HS, PAIR, CL>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        max_clusters = n;
+    }
+    if (max_clusters < 1) return SN_ERR_NOMEM;                                 // caller falls back to the single-CTA form
+    if ((int)grid.x > max_clusters * CL) cfg.gridDim.x = (unsigned)(max_clusters * CL);   // GPCs whose SM count is no multiple of CL leave SMs out
+    SN_CUDA((cudaLaunchKernelEx(&cfg, conv_wg_kernel<AD, N, OUT, HS, PAIR, CL>, map, p)));
     return SN_OK;
+}
+// cl = CTAs per weight-sharing cluster (1 or 2); a cluster launch that cannot be resident falls back to single CTAs
+template <int AD, int N, int OUT, bool HS, bool PAIR>
+static int wg_launch_t(const CUtensorMap& map, const ConvWgParams& p, dim3 grid, size_t smem, cudaStream_t stream, int cl = 1) {
+    if constexpr (!HS) {
+        if (cl == 2) {
+            const int rc = wg_launch_c<AD, N, OUT, HS, PAIR, 2>(map, p, grid, smem, stream);
+            if (rc != SN_ERR_NOMEM) return rc;
+        }
+    }
+    return wg_launch_c<AD, N, OUT, HS, PAIR, 1>(map, p, grid, smem, stream);
 }
 
 int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S, int out_fmt, __half* out, int cg_out_total, int cg_out_off,
@@ -900,10 +951,16 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     if (!n_sm) { int dev = 0; SN_CUDA(cudaGetDevice(&dev)); SN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     dim3 grid((unsigned)std::min<long long>(p.n_tiles, n_sm));               // persistent, one CTA per SM (TMEM: 512 columns)
     const size_t smem = std::max(cfg.smem, (size_t)(227 * 1024 / 2) + 1);     // never two CTAs per SM: the second would spin in tcgen05.alloc
+    // weight multicast over CTA pairs (SN_WG_CLUSTER=2; off by default: measured slower, see the kernel's header): both CTAs of a pair must see the same
+    // sequence of weight slots, i.e. the same number of tiles and the same N tile at every step -- tiles t = blockIdx.x + i * gridDim.x of neighbours
+    // (2k, 2k+1) with an even grid and an even tile count per N tile
+    static const int env_cl = getenv("SN_WG_CLUSTER") ? atoi(getenv("SN_WG_CLUSTER")) : 1;
+    const long long tiles_per_nt = (long long)n_pc * p.tiles_d * p.tiles_h;
+    const int cl = (env_cl == 2 && !p.hs && !p.dbg && grid.x % 2 == 0 && tiles_per_nt % 2 == 0) ? 2 : 1;
     rc = SN_ERR_INVALID;
 #define SN_WG_CASE(ad, nn, geo8, pr) if (cfg.AD == ad && N == nn && (p.hs != 0) == geo8 && (p.pair_last != 0) == pr) \
-        rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nn, WG_OUT_WINO, geo8, pr>(map, p, grid, smem, stream) : wg_launch_t<ad, nn, WG_OUT_RAW, geo8, pr>(map, p, grid, smem, stream)
-    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112 && !p.hs && p.pair_last) rc = wg_launch_t<1, 112, WG_OUT_FINAL, false, true>(map, p, grid, smem, stream); }
+        rc = (out_fmt == WG_OUT_WINO) ? wg_launch_t<ad, nn, WG_OUT_WINO, geo8, pr>(map, p, grid, smem, stream, cl) : wg_launch_t<ad, nn, WG_OUT_RAW, geo8, pr>(map, p, grid, smem, stream, cl)
+    if (out_fmt == WG_OUT_FINAL) { if (cfg.AD == 1 && N == 112 && !p.hs && p.pair_last) rc = wg_launch_t<1, 112, WG_OUT_FINAL, false, true>(map, p, grid, smem, stream, cl); }
     else {
         SN_WG_CASE(4, 32, false, false); SN_WG_CASE(4, 32, false, true); SN_WG_CASE(2, 32, false, false); SN_WG_CASE(2, 32, false, true);
         SN_WG_CASE(1, 80, false, false); SN_WG_CASE(1, 112, false, false); SN_WG_CASE(1, 112, false, true);

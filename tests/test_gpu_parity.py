@@ -712,8 +712,9 @@ def test_forward_with_fused_side_epilogue_subprocess(torch_cuda):
 
 
 def test_fused_passes_are_bit_identical_to_the_separate_ones(torch_cuda, params, cams, tmp_path):
-    """The default chain (images -> conv1_1's operand in one pass; side_op1 + pool1 in one pass over conv1_3's output) against the
-    separate passes it replaces (SN_CVC_FUSED=0 SN_SIDE_POOL=0: cvc_gather + pack_wino, side_wino + pool_blk), in a child process
+    """The default chain (images -> conv1_1's operand in one pass; side_op1 + pool1 in one pass over conv1_3's output) against the separate
+    passes it replaces (SN_CVC_FUSED=0 SN_SIDE_POOL=0: cvc_gather + pack_wino, side_wino + pool_blk), the latter also with the opt-in form of
+    the Winograd units as CTA pairs sharing one multicast weight stream (SN_WG_CLUSTER=2), in a child process
     because the switches are read once: probabilities, float16 predictions and votes must be the SAME bits, 64^3 and 32^3."""
     import os, subprocess, sys
     body = ("import sys; sys.path.insert(0, %r)\n"
@@ -729,7 +730,7 @@ def test_fused_passes_are_bit_identical_to_the_separate_ones(torch_cuda, params,
             "    hp = hp or pipeline.HotPath(SurfaceNet.Net(weights.synthetic_params(0)), DeviceScene(cams, imgs))\n"
             "    o = hp.infer_batch_host(pairs, xyz, resol, w, D)\n"
             "    np.savez(sys.argv[1] + '_%%d.npz' %% D, fused=o['fused'], pred16=o['pred16'], votes=o['votes'])\n" % util.REPO)
-    for tag, env in (("fused", {}), ("separate", {"SN_CVC_FUSED": "0", "SN_SIDE_POOL": "0"})):
+    for tag, env in (("fused", {}), ("separate", {"SN_CVC_FUSED": "0", "SN_SIDE_POOL": "0", "SN_WG_CLUSTER": "2"})):
         out = subprocess.run([sys.executable, "-c", body, str(tmp_path / tag)], env=dict(os.environ, **env), stdout=subprocess.PIPE,
                              stderr=subprocess.PIPE, text=True, timeout=900)
         assert out.returncode == 0, out.stderr[-2000:]

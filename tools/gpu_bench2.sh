@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU bench (NCCL gather of float16 + votes, c4 shard) -- run with gpurun --gpus 2
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 6 --warmup 3 --c4-shard > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 6 --warmup 3 > gpurun_out/r02_bench_n2.json 2> gpurun_out/r02_bench_n2.err
 python - <<'PY'
 import json
 try:

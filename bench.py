@@ -15,7 +15,8 @@ synthetic uint8 1200x1600 images, synthetic calibrated weights.  Weak scaling: e
 are all-gathered ONCE per step, inside the timed region; the float16 gather runs under the ray-pool kernels.
 At 8 GPUs (or with --c4-shard) the line also carries "c4_shard": one BASELINE configs[3] shard (64 cubes x 8 view pairs per GPU).
 
-value  = fused surface-probability voxels / s, whole job, inputs resident in HBM (device timed, max over ranks)
+value  = fused surface-probability voxels / s, whole job, inputs resident in HBM (device timed, max over ranks); taken from a plain
+         pass of K steps -- a second pass of K steps carries the per-launch CUDA events of the conv units for `roofline`
 e2e    = same metric through HotPath.infer_batch_host: pinned HOST per-batch arguments in, fused f32 +
          float16 prediction + votes back to pinned host memory, copies inside the timed region.
 """
@@ -359,7 +360,10 @@ def run_gpu(args, wl):
             got = hp.infer_batch_host(ref["pairs"], ref["xyz"], ref["resol"], ref["w"], D)
             line["parity_check"] = {"case": "the cpu_baseline cube (1 cube x %d view-pairs of %d^3), mode %s" % (n_vp, D, mode),
                                     "max_abs_prob_vs_port": float(np.abs(got["fused"] - ref["fused"]).max()), "tolerance": 1e-4,
-                                    "votes_differing_voxels": int((got["votes"] != ref["votes"]).sum()), "voxels": int(V)}
+                                    "votes_differing_voxels": int((got["votes"] != ref["votes"]).sum()), "voxels": int(V),
+                                    "votes_note": "votes are counted on the float16 cast of each side's OWN probabilities: a difference <= tolerance can flip a "
+                                                  "float16 rounding next to min_prob or a ray's arg-max; the vote logic itself is bit-exact on equal inputs "
+                                                  "(tests/test_gpu_parity.py::test_infer_batch_host_matches_oracle_pipeline, test_raypool_*)"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -156,6 +156,8 @@ int sn_cast_f32_to_f16(const float* in_dev, int64_t n, void* out_f16_dev, void* 
  * the device: CVC gather (+mean) -> SurfaceNet -> view-pair fusion -> float16 cast -> ray-pool votes.
  *   outputs: fused_out_dev (B,1,D,D,D) f32, unfused_out_dev (B,n_vp,D,D,D) f32 or NULL,
  *            pred16_out_dev (B,D,D,D) f16, votes_out_dev (B,D,D,D) u8 or NULL (skip ray pooling)
+ * In the default mode at D = 16 / 32 / 64 the gather writes the first unit's operand directly (no fp32 CVC tensor in
+ * HBM); the bits are those of sn_cvc_gather followed by sn_net_forward.
  */
 int64_t sn_infer_batch_workspace_bytes(const sn_net* net, int n_cubes, int n_vp, int D, int mode);
 int sn_infer_batch(const sn_net* net, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
@@ -166,8 +168,9 @@ int sn_infer_batch(const sn_net* net, const uint8_t* images_dev, const int64_t* 
 
 /* same, HOST buffers for the per-batch arguments and results (images / cameras / weights stay
  * resident on the device, as they are per-scene constants: main_reconstruct.py:49-51,70-72).
- * Copies in: xyz, resol, viewpairs, w.  Copies out: fused f32, pred16, votes (each may be NULL).
- * Synchronises `stream` before returning. */
+ * Copies in: xyz, resol, viewpairs, w.  Copies out: fused f32, pred16, votes (each may be NULL); with votes requested the
+ * two probability volumes leave on an internal side stream while ray pooling still runs on `stream`.
+ * Synchronises `stream` (which waits for the side stream) before returning. */
 int sn_infer_batch_host(const sn_net* net, const uint8_t* images_dev, const int64_t* img_offset_dev, const int32_t* img_hw_dev,
                         int n_views, const double* P_dev, const float* xyz_host, const float* resol_host,
                         const int32_t* viewpairs_host, const float* w_host, int n_cubes, int n_vp, int D, float min_prob_f16,

@@ -1,6 +1,8 @@
 #!/bin/bash
 # round 2, second session: fused gather / side+pool / ray-pool table sizing / D2H side stream -- targeted tests with hang guards, then an
-# interleaved A/B of the new build against the previous one (tools/ab/lib_r2a.so) on the same box
+# interleaved A/B of the new build against the previous one (tools/ab/lib_r2a.so) on the same box.  The other library is not tracked (*.so); rebuild it with
+#   mkdir -p gpurun_out/oldbuild && git archive <rev> surfacenet_b200/csrc include | tar -x -C gpurun_out/oldbuild &&
+#   make -C gpurun_out/oldbuild/surfacenet_b200/csrc && mkdir -p tools/ab && cp gpurun_out/oldbuild/surfacenet_b200/libsurfacenet_b200.so tools/ab/lib_r2a.so
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "raypool" > gpurun_out/r2b_first.log 2>&1
 rc=$?; echo "raypool exit $rc"; tail -3 gpurun_out/r2b_first.log

@@ -512,3 +512,19 @@ def test_readPointCloud_xyz_formats(tmp_path):
     a, _ = reconstruct.quantize_pts_to_cubes(sparseCubes.readPointCloud_xyz(str(tmp_path / "pts.ply")), np.float32(0.4), 32, 26, 0.5)
     b, _ = reconstruct.quantize_pts_to_cubes(pts, np.float32(0.4), 32, 26, 0.5)
     assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["ijk"], b["ijk"])
+
+
+def test_fast_mode_warns_and_exact_is_the_default():
+    """the single-pass fp16 mode misses the 1e-4 bound by ~100x -- selecting it must be loud; no environment variable may
+    switch the default of the drop-ins away from the parity mode."""
+    import warnings
+    from surfacenet_b200 import _lib
+    assert _lib.DEFAULT_MODE == "exact"
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert _lib.resolve_mode("exact") == _lib.MODE_TC_EXACT and _lib.resolve_mode("fp32") == _lib.MODE_FP32
+        assert not rec
+        assert _lib.resolve_mode("fast") == _lib.MODE_TC_FAST
+        assert len(rec) == 1 and issubclass(rec[0].category, RuntimeWarning) and "1e-4" in str(rec[0].message)
+    with pytest.raises((KeyError, ValueError)):
+        _lib.resolve_mode("bf16")

@@ -913,6 +913,11 @@ int wg_conv_launch(const Net& net, int u, const __half* in_wino, int n_pc, int S
     ConvWgParams p{};
     p.S = S; p.n_pc = n_pc; p.dil = cu.dil; p.n_cblk = wu.n_cblk; p.cg_in = cg_in_total ? cg_in_total : wu.Cin_pad / 8;
     static const int env_dbg = getenv("SN_WG_DEBUG") ? atoi(getenv("SN_WG_DEBUG")) : 0;
+    static bool dbg_warned = false;
+    if (env_dbg && !dbg_warned) {                        // a timing knob must never pass for a result silently
+        dbg_warned = true;
+        fprintf(stderr, "surfacenet_b200: SN_WG_DEBUG=%d is set -- the Winograd units skip work for TIMING experiments, their outputs are NOT valid\n", env_dbg);
+    }
     p.dbg = env_dbg;
     static const int env_order = getenv("SN_WG_ORDER") ? atoi(getenv("SN_WG_ORDER")) : 1;       // measured: 67.4 vs 68.5 ms per C3 step
     p.d_fastest = env_order;
